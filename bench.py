@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the batched sequence path (BASELINE.json):
+
+  workload (N=1): configs[1] — contains_seq of a 1 Gbp synthetic FASTA (1000 records x 1 Mbp, every
+  other record a copy of an index record => ~50 % hits) against a 500M-k-mer index (500 records x
+  1 Mbp), K=25, T=u64, PREFIX_BITS=24, one B200.  One "step" = one contains_seq pass over the whole
+  query batch.  insert_seq throughput (the index build) is reported alongside in `extra`.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Prints ONE JSON line (see the task contract): value = k-mers/s with the query resident in HBM
+(CUDA events on the library's stream), e2e = the same through the host-buffer C-ABI call
+(cbl_contains_seqs: pinned host memory in, answers out, copies inside the timed region),
+roofline for the dominant kernel, cpu_baseline = the CPU oracle timed on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K, T_BITS, PREFIX_BITS = 25, 64, 24
+METRIC = "contains_seq k-mers/s (K=25, u64, PREFIX_BITS=24; 1 Gbp query vs 500M-k-mer index)"
+UNIT = "k-mers/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--index-mbp", type=float, default=500.0, help="index size in Mbp (per GPU when N>1)")
+    ap.add_argument("--query-mbp", type=float, default=1000.0, help="query size in Mbp per step (per GPU when N>1)")
+    ap.add_argument("--record-bp", type=int, default=1_000_000)
+    ap.add_argument("--cpu-index-mbp", type=float, default=20.0, help="CPU baseline sample: index size")
+    ap.add_argument("--cpu-query-mbp", type=float, default=10.0, help="CPU baseline sample: query size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data (uniform ACGT, seeded).  numpy on the host: used by the CPU legs and tiny runs.
+# ------------------------------------------------------------------------------------------------
+BASES = np.frombuffer(b"ACTG", dtype=np.uint8)
+
+
+def host_dna(n: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return BASES[rng.integers(0, 4, size=n, dtype=np.uint8)]
+
+
+def device_dna(torch, n: int, seed: int, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lut = torch.tensor(list(b"ACTG"), dtype=torch.uint8, device=device)
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    step = 1 << 26
+    for s in range(0, n, step):
+        m = min(step, n - s)
+        codes = torch.randint(0, 4, (m,), generator=g, device=device, dtype=torch.int32)
+        out[s : s + m] = lut[codes]
+    return out
+
+
+def make_workload(torch, device, index_bp: int, query_bp: int, rec: int, seed_base: int):
+    """index = n_i records; query = n_q records where even records are copies of index records
+    (hits) and odd records are fresh (misses)."""
+    n_i, n_q = max(1, index_bp // rec), max(1, query_bp // rec)
+    index = device_dna(torch, n_i * rec, seed_base + 2, device)
+    query = device_dna(torch, n_q * rec, seed_base + 3, device)
+    iv, qv = index.view(n_i, rec), query.view(n_q, rec)
+    for q in range(0, n_q, 2):
+        qv[q].copy_(iv[(q // 2) % n_i])
+    i_off = np.arange(n_i + 1, dtype=np.uint64) * np.uint64(rec)
+    q_off = np.arange(n_q + 1, dtype=np.uint64) * np.uint64(rec)
+    return index, i_off, query, q_off
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the oracle is the checker / baseline, never the product)
+# ------------------------------------------------------------------------------------------------
+def cpu_leg(index_mbp: float, query_mbp: float, rec: int, steps: int = 1, warmup: int = 0):
+    from oracle import pyoracle
+
+    L = pyoracle.load()
+    kind_note = "restated reference (C++ port of the Rust path) linked against the reference's own sux/tiered-vector C++" if L.orc_uses_reference_cxx() else "restated reference (C++ port), stand-in bitvector/tiered vector"
+    rec = min(rec, 1_000_000)
+    n_i, n_q = max(1, int(index_mbp * 1e6) // rec), max(1, int(query_mbp * 1e6) // rec)
+    index = np.concatenate([host_dna(rec, 1000 + i) for i in range(n_i)])
+    qrecs = [index[(q // 2 % n_i) * rec : (q // 2 % n_i + 1) * rec] if q % 2 == 0 else host_dna(rec, 5000 + q) for q in range(n_q)]
+    query = np.concatenate(qrecs)
+    i_off = np.arange(n_i + 1, dtype=np.uint64) * np.uint64(rec)
+    q_off = np.arange(n_q + 1, dtype=np.uint64) * np.uint64(rec)
+    o = pyoracle.OracleCBL(K, T_BITS, PREFIX_BITS, lib=L)
+    t_ins = o.time_insert_seqs(index, i_off)
+    n_ins = n_i * (rec - K + 1)
+    n_q_kmers = n_q * (rec - K + 1)
+    times = []
+    for s in range(warmup + steps):
+        t, pos = o.time_contains_seqs(query, q_off)
+        if s >= warmup:
+            times.append(t)
+    t_q = float(np.mean(times))
+    return {
+        "contains_kmers_per_s": n_q_kmers / t_q,
+        "insert_kmers_per_s": n_ins / t_ins,
+        "ms_per_step": 1e3 * t_q,
+        "sample": f"index {n_i} x {rec} bp ({n_ins} k-mers, build {t_ins:.1f} s), query {n_q} x {rec} bp per step (50% hit records), 1 thread",
+        "kind_note": kind_note,
+        "positives": pos,
+        "n_q_kmers": n_q_kmers,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (restated oracle; the Rust
+    crate cannot be built in this image), single-threaded because the reference is."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_leg(args.cpu_index_mbp, args.cpu_query_mbp, args.record_bp, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["contains_kmers_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[1] contains_seq, K=25 u64 PREFIX_BITS=24 (bounded CPU sample)", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["contains_kmers_per_s"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["sample"], "note": r["kind_note"],
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": r["contains_kmers_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "extra": {"insert_seq_kmers_per_s": r["insert_kmers_per_s"]},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import cbl_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU leg")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    rec = args.record_bp
+    index_bp, query_bp = int(args.index_mbp * 1e6), int(args.query_mbp * 1e6)
+
+    if world > 1:
+        from cbl_b200.sharded import ShardedCBL
+
+        cbl = ShardedCBL(K, T_BITS, PREFIX_BITS, canonical=False, device=local)
+    else:
+        cbl = cbl_b200.CBL(K, T_BITS, PREFIX_BITS, canonical=False, device=local)
+    index, i_off, query, q_off = make_workload(torch, device, index_bp, query_bp, rec, seed_base=100 * rank)
+    n_q_kmers = (len(q_off) - 1) * (rec - K + 1)
+    n_i_kmers = (len(i_off) - 1) * (rec - K + 1)
+    answers = torch.empty(n_q_kmers, dtype=torch.uint8, device=device)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- build (insert_seq) ----
+    barrier()
+    t0 = time.perf_counter()
+    cbl.insert_seqs_dev(index.data_ptr(), i_off)
+    barrier()
+    t_build = time.perf_counter() - t0
+    stored = cbl.count()
+    nb = cbl.num_buckets()
+
+    # ---- timed contains_seq steps (query resident in HBM) ----
+    def step():
+        cbl.contains_seqs_dev(query.data_ptr(), q_off, answers.data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = cbl_b200.launch_count()
+    cbl_b200.profile_enable(True)
+    cbl_b200.profile_report()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.ExternalStream(cbl.stream_ptr(), device=device)  # the stream the kernels are launched on
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    prof = cbl_b200.profile_report()
+    cbl_b200.profile_enable(False)
+    launches = cbl_b200.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    # device time between two events on the library's own stream (each call is synchronous, so the
+    # host wall time of the region is reported next to it as a cross-check)
+    elapsed = dev_ms / 1e3
+    if world > 1:
+        t = torch.tensor([elapsed], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    hits = int(answers.sum(dtype=torch.int64).item())
+    total_q = n_q_kmers * world
+    value = total_q * args.steps / elapsed
+
+    # ---- roofline of the dominant kernel (fused encode + necklace + probe) ----
+    peak, peak_src = peaks()
+    dom = None
+    for name, rec_ in prof.items():
+        if "seq_words_kernel" in name and (dom is None or rec_["ms"] > prof[dom]["ms"]):
+            dom = name
+    roof = None
+    if dom:
+        ms_per_launch = prof[dom]["ms"] / max(1, prof[dom]["n"])
+        bbar = stored / max(1, nb)
+        steps_bs = math.ceil(math.log2(bbar + 1))
+        bytes_per_kmer = 1 + 1 + 8 + steps_bs * 32
+        kmers_per_launch = n_q_kmers * args.steps / max(1, prof[dom]["n"])
+        achieved = bytes_per_kmer * kmers_per_launch / (ms_per_launch * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": dom, "ms_per_launch": ms_per_launch, "peak_source": peak_src,
+                "algorithmic_bytes_per_kmer": bytes_per_kmer,
+                "model": f"1 B ASCII in + 1 B answer out + 8 B bucket offsets + ceil(log2(b+1))={steps_bs} binary-search sectors x 32 B (mean bucket b={bbar:.1f}); realised branch of SURVEY 8d probe",
+                "kernel_share_of_step": prof[dom]["ms"] / (elapsed * 1e3)}
+
+    # ---- e2e: host buffers through the C ABI (pinned memory; H2D + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        h_query = torch.empty(query.numel(), dtype=torch.uint8, pin_memory=True)
+        h_query.copy_(query)
+        h_ans = torch.empty(n_q_kmers, dtype=torch.uint8, pin_memory=True)
+        hq, ha = h_query.numpy(), h_ans.numpy()
+        for _ in range(min(args.warmup, 2)):
+            cbl.contains_seqs(hq, q_off, out=ha)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cbl.contains_seqs(hq, q_off, out=ha)
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        assert int(ha.sum(dtype=np.int64)) == hits, "e2e answers differ from the device-resident run"
+        e2e = {"value": total_q * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(query.numel()) * world,
+               "d2h_bytes_per_step": int(n_q_kmers) * world, "ms_per_step": 1e3 * t_e2e / args.steps}
+
+    # ---- CPU baseline (rank 0, bounded sample) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_leg(args.cpu_index_mbp, args.cpu_query_mbp, rec)
+        cpu = {"value": r["contains_kmers_per_s"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["sample"], "note": r["kind_note"],
+               "insert_seq_kmers_per_s": r["insert_kmers_per_s"], "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "configs[1]: contains_seq of 1 Gbp synthetic FASTA vs 500M-k-mer index, K=25, T=u64, PREFIX_BITS=24",
+                       "index_records": len(i_off) - 1, "query_records": len(q_off) - 1, "record_bp": rec, "per_gpu": world > 1,
+                       "stored_kmers": stored, "buckets": nb, "hit_fraction": hits / max(1, n_q_kmers),
+                       "l2_policy": f"inputs larger than L2: {query.numel() / 1e6:.0f} MB query + {stored * 4 / 1e6:.0f} MB index per step",
+                       "parallelism": "1 GPU" if world == 1 else f"prefix-range sharded x{world}, one all-to-all per batch"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "extra": {"wall_s_timed_region": wall, "insert_seq_kmers_per_s": n_i_kmers * world / t_build, "build_s": t_build, "kernel_ms": prof},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

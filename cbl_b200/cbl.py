@@ -1,0 +1,371 @@
+"""Host-side mirror of the reference's public type ``CBL<K, T, PREFIX_BITS>`` (src/cbl.rs:40-569) on
+top of the C ABI (include/cbl_gpu.h).  Method names, argument meaning and error behaviour follow the
+reference: where the Rust code panics this raises ``CBLError`` with the same message.
+
+The Rust toolchain is absent from the build image, so this Python class (and the C++ facade
+include/cbl.hpp) stand where the reference's ``src/cbl.rs`` would sit above the ABI; INTEGRATION.md
+shows the Rust binding.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import u8p, u32p, u64p
+
+Seq = Union[bytes, bytearray, memoryview, np.ndarray]
+
+OP_OR, OP_AND, OP_SUB, OP_XOR = 0, 1, 2, 3
+
+
+class CBLError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+
+
+def _as_u8(seq: Seq) -> np.ndarray:
+    if isinstance(seq, np.ndarray):
+        if seq.dtype != np.uint8:
+            raise TypeError("sequence arrays must be uint8")
+        return np.ascontiguousarray(seq)
+    return np.frombuffer(bytes(seq) if not isinstance(seq, (bytes, bytearray)) else seq, dtype=np.uint8)
+
+
+def _split_kmers(kmers: Iterable[int]) -> Tuple[np.ndarray, np.ndarray]:
+    ks = list(kmers)
+    lo = np.fromiter((k & 0xFFFFFFFFFFFFFFFF for k in ks), dtype=np.uint64, count=len(ks))
+    hi = np.fromiter(((k >> 64) & 0xFFFFFFFFFFFFFFFF for k in ks), dtype=np.uint64, count=len(ks))
+    return lo, hi
+
+
+def concat_records(records: Sequence[Seq]) -> Tuple[np.ndarray, np.ndarray]:
+    arrs = [_as_u8(r) for r in records]
+    offsets = np.zeros(len(arrs) + 1, dtype=np.uint64)
+    if arrs:
+        offsets[1:] = np.cumsum([len(a) for a in arrs], dtype=np.uint64)
+    buf = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.uint8)
+    return buf, offsets
+
+
+class CBL:
+    """A fully dynamic set of k-mers resident in the memory of one B200.
+
+    ``CBL(k, t_bits, prefix_bits=24)`` ~ ``CBL::<K, T, PREFIX_BITS>::new()``;
+    ``CBL.new_canonical(k, t_bits, prefix_bits)`` ~ ``::new_canonical()``.
+    """
+
+    def __init__(self, k: int, t_bits: int, prefix_bits: int = 24, canonical: bool = False, device: int = 0, *, _handle=None):
+        self._L = _lib.lib()
+        self.k, self.t_bits, self.prefix_bits, self.device = k, t_bits, prefix_bits, device
+        if _handle is not None:
+            self._h = _handle
+            return
+        h = C.c_void_p()
+        rc = self._L.cbl_create(k, t_bits, prefix_bits, int(canonical), device, C.byref(h))
+        if rc:
+            raise CBLError(rc, self._L.cbl_last_global_error().decode())
+        self._h = h
+
+    @classmethod
+    def new_canonical(cls, k: int, t_bits: int, prefix_bits: int = 24, device: int = 0) -> "CBL":
+        return cls(k, t_bits, prefix_bits, True, device)
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def _wrap(self, h) -> "CBL":
+        return CBL(self.k, self.t_bits, self.prefix_bits, device=self.device, _handle=h)
+
+    def _chk(self, rc: int):
+        if rc:
+            raise CBLError(rc, self._L.cbl_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cbl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    # -- scalar queries (src/cbl.rs:162-177) -----------------------------------------------------
+    def is_canonical(self) -> bool:
+        v = C.c_int32()
+        self._chk(self._L.cbl_is_canonical(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def count(self) -> int:
+        v = C.c_uint64()
+        self._chk(self._L.cbl_count(self._h, C.byref(v)))
+        return int(v.value)
+
+    def __len__(self) -> int:
+        return self.count()
+
+    def is_empty(self) -> bool:
+        v = C.c_int32()
+        self._chk(self._L.cbl_is_empty(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def num_buckets(self) -> int:
+        v = C.c_uint64()
+        self._chk(self._L.cbl_num_buckets(self._h, C.byref(v)))
+        return int(v.value)
+
+    def word_bytes(self) -> int:
+        v = C.c_int32()
+        self._chk(self._L.cbl_word_bytes(self._h, C.byref(v)))
+        return int(v.value)
+
+    def clone(self) -> "CBL":
+        h = C.c_void_p()
+        self._chk(self._L.cbl_clone(self._h, C.byref(h)))
+        return self._wrap(h)
+
+    # -- sequences (src/cbl.rs:293-354) ----------------------------------------------------------
+    def insert_seq(self, seq: Seq) -> None:
+        a = _as_u8(seq)
+        self._chk(self._L.cbl_insert_seq(self._h, a.ctypes.data, len(a)))
+
+    def remove_seq(self, seq: Seq) -> None:
+        a = _as_u8(seq)
+        self._chk(self._L.cbl_remove_seq(self._h, a.ctypes.data, len(a)))
+
+    def contains_seq(self, seq: Seq) -> np.ndarray:
+        a = _as_u8(seq)
+        out = np.zeros(max(len(a) - self.k + 1, 1), dtype=np.uint8)
+        n = C.c_size_t()
+        self._chk(self._L.cbl_contains_seq(self._h, a.ctypes.data, len(a), out.ctypes.data, C.byref(n)))
+        return out[: n.value].astype(bool)
+
+    def contains_all(self, seq: Seq) -> bool:
+        a = _as_u8(seq)
+        v = C.c_int32()
+        self._chk(self._L.cbl_contains_all(self._h, a.ctypes.data, len(a), C.byref(v)))
+        return bool(v.value)
+
+    # batches of records: one ABI call for the whole `for record in reader` loop of examples/cbl.rs
+    def insert_seqs(self, buf: np.ndarray, offsets: np.ndarray) -> None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._chk(self._L.cbl_insert_seqs(self._h, buf.ctypes.data, offsets.ctypes.data_as(u64p), len(offsets) - 1))
+
+    def remove_seqs(self, buf: np.ndarray, offsets: np.ndarray) -> None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._chk(self._L.cbl_remove_seqs(self._h, buf.ctypes.data, offsets.ctypes.data_as(u64p), len(offsets) - 1))
+
+    def count_kmers(self, offsets: np.ndarray) -> int:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        v = C.c_uint64()
+        self._chk(self._L.cbl_count_kmers(self._h, offsets.ctypes.data_as(u64p), len(offsets) - 1, C.byref(v)))
+        return int(v.value)
+
+    def contains_seqs(self, buf: np.ndarray, offsets: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = self.count_kmers(offsets)
+        if out is None:
+            out = np.zeros(max(n, 1), dtype=np.uint8)
+        self._chk(self._L.cbl_contains_seqs(self._h, buf.ctypes.data, offsets.ctypes.data_as(u64p), len(offsets) - 1, out.ctypes.data))
+        return out[:n]
+
+    # device-resident buffers: raw device pointers (e.g. torch_tensor.data_ptr())
+    def insert_seqs_dev(self, d_buf: int, offsets: np.ndarray) -> None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._chk(self._L.cbl_insert_seqs_dev(self._h, d_buf, offsets.ctypes.data_as(u64p), len(offsets) - 1))
+
+    def remove_seqs_dev(self, d_buf: int, offsets: np.ndarray) -> None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._chk(self._L.cbl_remove_seqs_dev(self._h, d_buf, offsets.ctypes.data_as(u64p), len(offsets) - 1))
+
+    def contains_seqs_dev(self, d_buf: int, offsets: np.ndarray, d_out: int) -> None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._chk(self._L.cbl_contains_seqs_dev(self._h, d_buf, offsets.ctypes.data_as(u64p), len(offsets) - 1, d_out))
+
+    def seq_words_dev(self, d_buf: int, offsets: np.ndarray, d_words: int) -> None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._chk(self._L.cbl_seq_words_dev(self._h, d_buf, offsets.ctypes.data_as(u64p), len(offsets) - 1, d_words))
+
+    def words_op_dev(self, op: int, d_words: int, n: int, d_out: int = 0) -> None:
+        self._chk(self._L.cbl_words_op_dev(self._h, op, d_words, n, d_out))
+
+    def export_words_dev(self, start: int, count: int, d_out: int) -> None:
+        self._chk(self._L.cbl_export_words_dev(self._h, start, count, d_out))
+
+    # -- single k-mers (src/cbl.rs:219-235); k-mers are IntKmer integers -------------------------
+    def _kmers(self, fn, kmers: Iterable[int], want: bool) -> np.ndarray:
+        lo, hi = _split_kmers(kmers)
+        out = np.zeros(max(len(lo), 1), dtype=np.uint8)
+        self._chk(fn(self._h, lo.ctypes.data_as(u64p), hi.ctypes.data_as(u64p), len(lo), out.ctypes.data if want else None))
+        return out[: len(lo)].astype(bool)
+
+    def contains(self, kmer: int) -> bool:
+        return bool(self._kmers(self._L.cbl_contains_kmers, [kmer], True)[0])
+
+    def insert(self, kmer: int) -> bool:
+        """Returns True if the k-mer was absent (src/cbl.rs:226-228)."""
+        return not bool(self._kmers(self._L.cbl_insert_kmers, [kmer], True)[0])
+
+    def remove(self, kmer: int) -> bool:
+        """Returns True if the k-mer was present (src/cbl.rs:233-235)."""
+        return bool(self._kmers(self._L.cbl_remove_kmers, [kmer], True)[0])
+
+    def contains_kmers(self, kmers: Iterable[int]) -> np.ndarray:
+        return self._kmers(self._L.cbl_contains_kmers, kmers, True)
+
+    def insert_kmers(self, kmers: Iterable[int]) -> np.ndarray:
+        """Inserts all; returns, per k-mer, whether it was in the set before the call."""
+        return self._kmers(self._L.cbl_insert_kmers, kmers, True)
+
+    def remove_kmers(self, kmers: Iterable[int]) -> np.ndarray:
+        return self._kmers(self._L.cbl_remove_kmers, kmers, True)
+
+    # -- iteration (src/cbl.rs:358-360): ascending word order ------------------------------------
+    def _export(self, fn, chunk: int = 1 << 20) -> Iterator[Tuple[np.ndarray, np.ndarray]]:
+        start, total = 0, self.count()
+        lo = np.zeros(min(chunk, max(total, 1)), dtype=np.uint64)
+        hi = np.zeros_like(lo)
+        n = C.c_size_t()
+        while start < total:
+            self._chk(fn(self._h, start, lo.ctypes.data_as(u64p), hi.ctypes.data_as(u64p), len(lo), C.byref(n)))
+            if n.value == 0:
+                break
+            yield lo[: n.value].copy(), hi[: n.value].copy()
+            start += n.value
+
+    def words(self) -> List[int]:
+        """All stored words (necklace << POS_BITS | pos), ascending."""
+        out: List[int] = []
+        for lo, hi in self._export(self._L.cbl_export_words):
+            out.extend(int(a) | (int(b) << 64) for a, b in zip(lo, hi))
+        return out
+
+    def words_arrays(self) -> Tuple[np.ndarray, np.ndarray]:
+        parts = list(self._export(self._L.cbl_export_words))
+        if not parts:
+            return np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64)
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    def iter(self) -> Iterator[int]:
+        """The stored k-mers as IntKmer integers (in canonical mode: the even-parity representative)."""
+        for lo, hi in self._export(self._L.cbl_export_kmers):
+            for a, b in zip(lo, hi):
+                yield int(a) | (int(b) << 64)
+
+    __iter__ = iter
+
+    def buckets_sizes(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(prefix, bucket size) pairs in ascending prefix order (src/cbl.rs:370-372)."""
+        n = C.c_size_t()
+        self._chk(self._L.cbl_bucket_sizes(self._h, None, None, 0, C.byref(n)))
+        p = np.zeros(max(n.value, 1), dtype=np.uint32)
+        s = np.zeros(max(n.value, 1), dtype=np.uint32)
+        if n.value:
+            self._chk(self._L.cbl_bucket_sizes(self._h, p.ctypes.data_as(u32p), s.ctypes.data_as(u32p), len(p), C.byref(n)))
+        return p[: n.value], s[: n.value]
+
+    def prefix_load(self) -> float:
+        return self.num_buckets() / float(1 << self.prefix_bits)  # src/wordset/mod.rs:254-256
+
+    # -- set operations (src/cbl.rs:411-569, 108-124) --------------------------------------------
+    def _binary(self, op: int, other: "CBL") -> "CBL":
+        h = C.c_void_p()
+        self._chk(self._L.cbl_setop(op, self._h, other._h, C.byref(h)))
+        return self._wrap(h)
+
+    def _assign(self, op: int, other: "CBL") -> "CBL":
+        self._chk(self._L.cbl_setop_assign(op, self._h, other._h))
+        return self
+
+    def __or__(self, o): return self._binary(OP_OR, o)
+    def __and__(self, o): return self._binary(OP_AND, o)
+    def __sub__(self, o): return self._binary(OP_SUB, o)
+    def __xor__(self, o): return self._binary(OP_XOR, o)
+    def __ior__(self, o): return self._assign(OP_OR, o)
+    def __iand__(self, o): return self._assign(OP_AND, o)
+    def __isub__(self, o): return self._assign(OP_SUB, o)
+    def __ixor__(self, o): return self._assign(OP_XOR, o)
+
+    @staticmethod
+    def _many(fn_name: str, cbls: Sequence["CBL"]) -> "CBL":
+        if not cbls:
+            raise CBLError(1, "empty list of indexes")
+        arr = (C.c_void_p * len(cbls))(*[c._h for c in cbls])
+        h = C.c_void_p()
+        first = cbls[0]
+        first._chk(getattr(first._L, fn_name)(arr, len(cbls), C.byref(h)))
+        return first._wrap(h)
+
+    @staticmethod
+    def merge(cbls: Sequence["CBL"]) -> "CBL":
+        return CBL._many("cbl_merge_many", cbls)
+
+    @staticmethod
+    def intersect(cbls: Sequence["CBL"]) -> "CBL":
+        return CBL._many("cbl_intersect_many", cbls)
+
+    # -- serde (src/cbl.rs:127-160) --------------------------------------------------------------
+    def serialize(self) -> bytes:
+        n = C.c_size_t()
+        self._chk(self._L.cbl_serialize_size(self._h, C.byref(n)))
+        buf = np.zeros(max(n.value, 1), dtype=np.uint8)
+        self._chk(self._L.cbl_serialize(self._h, buf.ctypes.data, len(buf), C.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def deserialize(self, data: bytes) -> "CBL":
+        a = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        self._chk(self._L.cbl_deserialize(self._h, a.ctypes.data, len(a), C.byref(h)))
+        return self._wrap(h)
+
+    def save_to_file(self, path: str) -> None:
+        self._chk(self._L.cbl_save_to_file(self._h, path.encode()))
+
+    def load_from_file(self, path: str) -> "CBL":
+        """``CBL::<K,T,P>::load_from_file(path)``; K / T / PREFIX_BITS / device are taken from ``self``."""
+        h = C.c_void_p()
+        self._chk(self._L.cbl_load_from_file(self._h, path.encode(), C.byref(h)))
+        return self._wrap(h)
+
+    # -- diagnostics -----------------------------------------------------------------------------
+    def seq_words(self, records: Sequence[Seq], brute: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+        buf, offsets = concat_records(records)
+        n = self.count_kmers(offsets)
+        lo = np.zeros(max(n, 1), dtype=np.uint64)
+        hi = np.zeros(max(n, 1), dtype=np.uint64)
+        self._chk(self._L.cbl_seq_words(self._h, buf.ctypes.data, offsets.ctypes.data_as(u64p), len(offsets) - 1,
+                                        lo.ctypes.data_as(u64p), hi.ctypes.data_as(u64p), int(brute)))
+        return lo[:n], hi[:n]
+
+    def sync(self) -> None:
+        self._chk(self._L.cbl_sync(self._h))
+
+    def stream_ptr(self) -> int:
+        """The cudaStream_t every kernel of this handle is launched on (for CUDA-event timing)."""
+        return int(self._L.cbl_stream(self._h) or 0)
+
+
+def launch_count() -> int:
+    return int(_lib.lib().cbl_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    _lib.lib().cbl_profile_enable(int(on))
+
+
+def profile_report() -> dict:
+    """Per-kernel device time accumulated since the last report: {kernel: {"n": launches, "ms": total}}."""
+    import json
+
+    buf = C.create_string_buffer(1 << 16)
+    rc = _lib.lib().cbl_profile_report(buf, len(buf))
+    if rc:
+        raise CBLError(rc, _lib.lib().cbl_last_global_error().decode())
+    return json.loads(buf.value.decode())

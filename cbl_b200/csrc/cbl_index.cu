@@ -1,0 +1,704 @@
+// Host-side orchestration of one device-resident CBL shard: batches on a CUDA stream, the
+// sort -> unique -> probe -> directory rebuild -> merge pipeline, set operations and export.
+// B200 counterpart of src/cbl.rs + src/wordset/mod.rs (see DESIGN.md for the kernel map).
+#include "cbl_index.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "index_ops.cuh"
+#include "radix_sort.cuh"
+#include "seq_words.cuh"
+
+namespace cbl {
+
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+void prof_push(const char* tag, cudaEvent_t a, cudaEvent_t b) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back({tag, a, b});
+}
+// JSON object {"kernel": {"n": launches, "ms": total device ms}, ...}; clears the records
+std::string prof_report() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<uint64_t, double>> acc;
+    for (auto& r : g_prof_recs) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        std::string t;
+        for (const char* c = r.tag; *c; c++) if (*c != '(' && *c != ')' && *c != ' ') t.push_back(*c);
+        auto& e = acc[t];
+        e.first++;
+        e.second += ms;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof_recs.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : acc) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s\"%s\": {\"n\": %llu, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
+                 (unsigned long long)kv.second.first, kv.second.second);
+        out += buf;
+        first = false;
+    }
+    return out + "}";
+}
+
+static int pos_bits_for(int kmer_bits) {  // src/cbl.rs:66
+    int p = 0;
+    while ((1 << p) < kmer_bits) p++;
+    return p;
+}
+
+static uint64_t env_u64(const char* name, uint64_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return strtoull(v, nullptr, 10);
+}
+
+// One zeroed look-back workspace per kernel launch (status words + ticket counter).
+struct Lookback {
+    DevBuf<uint64_t> status;
+    DevBuf<uint32_t> counter;
+    Lookback(uint64_t tiles, cudaStream_t s) : status(tiles ? tiles : 1, s), counter(1, s) {
+        status.zero();
+        counter.zero();
+    }
+};
+
+template <class W, class Suf>
+class Index final : public IIndex {
+    Config cfg_;
+    KParams P_;
+    cudaStream_t st_ = nullptr;
+    cudaStream_t side_[2] = {nullptr, nullptr};
+    DevBuf<uint64_t> bitmap_;
+    DevBuf<uint32_t> blkrank_, bucket_prefix_, bucket_off_;
+    DevBuf<Suf> suf_;
+    uint32_t nb_ = 0;
+    uint64_t n_ = 0;
+    uint32_t last_prefix_ = 0;  // prefix of the last bucket (for the reference's is_empty quirk)
+    uint64_t bitmap_words_ = 0, n_blocks_ = 0;
+    uint64_t batch_kmers_;
+
+public:
+    explicit Index(const Config& cfg) : cfg_(cfg) {
+        P_.k = cfg.k;
+        P_.bits = 2 * cfg.k;
+        P_.pos_bits = pos_bits_for(2 * cfg.k);
+        P_.prefix_bits = cfg.prefix_bits;
+        P_.suffix_bits = P_.bits + P_.pos_bits - cfg.prefix_bits;
+        P_.canonical = cfg.canonical;
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        for (auto& s : side_) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, cfg.device));
+        uint64_t thr = UINT64_MAX;
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        uint64_t bits = 1ull << cfg.prefix_bits;
+        if (bits < 256) bits = 256;
+        bitmap_words_ = bits / 64;
+        n_blocks_ = bits / 256;
+        bitmap_.alloc(bitmap_words_, st_);
+        bitmap_.zero();
+        blkrank_.alloc(n_blocks_, st_);
+        blkrank_.zero();
+        bucket_prefix_.alloc(1, st_);
+        bucket_off_.alloc(1, st_);
+        bucket_off_.zero();
+        suf_.alloc(1, st_);
+        batch_kmers_ = env_u64("CBL_BATCH_KMERS", sizeof(W) == 8 ? (1ull << 27) : (1ull << 26));
+        if (batch_kmers_ > RS_MAX_KEYS) batch_kmers_ = RS_MAX_KEYS;
+        if (batch_kmers_ < CHUNK_KMERS) batch_kmers_ = CHUNK_KMERS;
+        static bool attr_done = false;
+        if (!attr_done) {
+            CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_done = true;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    ~Index() override {
+        cudaSetDevice(cfg_.device);
+        bitmap_.release(); blkrank_.release(); bucket_prefix_.release(); bucket_off_.release(); suf_.release();
+        if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
+        for (auto& s : side_) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    }
+
+    const Config& config() const override { return cfg_; }
+    const KParams& params() const override { return P_; }
+    cudaStream_t stream() const override { return st_; }
+    uint64_t count() const override { return n_; }
+    uint32_t n_buckets() const override { return nb_; }
+    // WordSet::is_empty is prefixes.count() == 0 and RankBV::count_ones() ignores the last bit
+    // (src/wordset/mod.rs:57-60, cxx/rank_bv.h:34): a set holding only words with the
+    // all-ones prefix reports empty.  Reproduced for drop-in behaviour.
+    bool is_empty_reference_semantics() const override {
+        if (nb_ == 0) return true;
+        return nb_ == 1 && last_prefix_ == (uint32_t)((1ull << cfg_.prefix_bits) - 1);
+    }
+    void sync() override { CUDA_CHECK(cudaSetDevice(cfg_.device)); CUDA_CHECK(cudaStreamSynchronize(st_)); }
+
+    IndexView<Suf> view() const {
+        IndexView<Suf> v;
+        v.bitmap = bitmap_.get(); v.blkrank = blkrank_.get(); v.bucket_prefix = bucket_prefix_.get();
+        v.bucket_off = bucket_off_.get(); v.suf = suf_.get(); v.nb = nb_; v.n = n_;
+        return v;
+    }
+
+    IIndex* clone() override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        std::unique_ptr<Index> c(new Index(cfg_));
+        sync();
+        c->copy_state_from(*this);
+        c->sync();
+        return c.release();
+    }
+    void copy_state_from(const Index& o) {
+        nb_ = o.nb_; n_ = o.n_; last_prefix_ = o.last_prefix_;
+        CUDA_CHECK(cudaMemcpyAsync(bitmap_.get(), o.bitmap_.get(), bitmap_words_ * 8, cudaMemcpyDeviceToDevice, st_));
+        CUDA_CHECK(cudaMemcpyAsync(blkrank_.get(), o.blkrank_.get(), n_blocks_ * 4, cudaMemcpyDeviceToDevice, st_));
+        bucket_prefix_.alloc(nb_ ? nb_ : 1, st_);
+        bucket_off_.alloc((uint64_t)nb_ + 1, st_);
+        suf_.alloc(n_ ? n_ : 1, st_);
+        if (nb_) CUDA_CHECK(cudaMemcpyAsync(bucket_prefix_.get(), o.bucket_prefix_.get(), (size_t)nb_ * 4, cudaMemcpyDeviceToDevice, st_));
+        CUDA_CHECK(cudaMemcpyAsync(bucket_off_.get(), o.bucket_off_.get(), ((size_t)nb_ + 1) * 4, cudaMemcpyDeviceToDevice, st_));
+        if (n_) CUDA_CHECK(cudaMemcpyAsync(suf_.get(), o.suf_.get(), n_ * sizeof(Suf), cudaMemcpyDeviceToDevice, st_));
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // records -> pieces (2048-aligned slices so chunking is identical to src/cbl.rs:239-243)
+    // ------------------------------------------------------------------------------------------
+    static constexpr uint32_t PIECE_KMERS = CHUNK_KMERS * 8192;  // 16.7M k-mers per piece
+
+    void check_records(const uint64_t* offsets, size_t n_seqs) const {
+        for (size_t i = 0; i < n_seqs; i++) {
+            if (offsets[i + 1] < offsets[i]) throw Error(CBL_EINVAL, "record offsets must be non-decreasing");
+            uint64_t len = offsets[i + 1] - offsets[i];
+            if (len < (uint64_t)cfg_.k)  // src/cbl.rs:294-299,329-334
+                throw Error(CBL_EINVAL, "Sequence size (" + std::to_string(len) + ") is smaller than K (" + std::to_string(cfg_.k) + ")");
+        }
+    }
+    // pieces of records [r0, r1) — out offsets are k-mer ranks counted from record r0
+    void build_pieces(const uint64_t* offsets, size_t r0, size_t r1, PieceList& pl) const {
+        pl = PieceList();
+        pl.chunk0.push_back(0);
+        for (size_t r = r0; r < r1; r++) {
+            uint64_t nk = offsets[r + 1] - offsets[r] - (uint64_t)cfg_.k + 1;
+            for (uint64_t s = 0; s < nk; s += PIECE_KMERS) {
+                uint32_t m = (uint32_t)std::min<uint64_t>(PIECE_KMERS, nk - s);
+                pl.byte_off.push_back(offsets[r] + s);
+                pl.out_off.push_back(pl.n_kmers + s);
+                pl.kmers.push_back(m);
+                pl.n_chunks += div_up(m, CHUNK_KMERS);
+                pl.chunk0.push_back(pl.n_chunks);
+            }
+            pl.n_kmers += nk;
+        }
+    }
+
+    struct DevPieces {
+        DevBuf<uint64_t> byte_off, out_off, chunk0;
+        DevBuf<uint32_t> kmers;
+        SeqBatch batch;
+    };
+    // upload pieces [p0, p1) with out offsets rebased by out_base
+    void upload_pieces(const PieceList& pl, size_t p0, size_t p1, uint64_t out_base, const uint8_t* d_seq, uint64_t n_bytes,
+                       DevPieces& dp, cudaStream_t s) const {
+        size_t np = p1 - p0;
+        std::vector<uint64_t> out(np), ch(np + 1);
+        for (size_t i = 0; i < np; i++) { out[i] = pl.out_off[p0 + i] - out_base; ch[i] = pl.chunk0[p0 + i] - pl.chunk0[p0]; }
+        ch[np] = pl.chunk0[p1] - pl.chunk0[p0];
+        dp.byte_off.alloc(np, s); dp.out_off.alloc(np, s); dp.chunk0.alloc(np + 1, s); dp.kmers.alloc(np, s);
+        CUDA_CHECK(cudaMemcpyAsync(dp.byte_off.get(), pl.byte_off.data() + p0, np * 8, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(dp.out_off.get(), out.data(), np * 8, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(dp.chunk0.get(), ch.data(), (np + 1) * 8, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(dp.kmers.get(), pl.kmers.data() + p0, np * 4, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));  // `out`/`ch` are stack temporaries
+        dp.batch.seq = d_seq; dp.batch.seq_end = d_seq + n_bytes;
+        dp.batch.piece_byte = dp.byte_off.get(); dp.batch.piece_out = dp.out_off.get();
+        dp.batch.piece_kmers = dp.kmers.get(); dp.batch.piece_chunk0 = dp.chunk0.get();
+        dp.batch.n_pieces = (uint32_t)np; dp.batch.n_chunks = ch[np];
+    }
+
+    // launches the fused encode + necklace (+ probe) kernel; throws EINVAL on a non-ACGT byte
+    void run_seq_words(const SeqBatch& b, int mode, bool brute, W* d_words, uint8_t* d_flags, cudaStream_t s) {
+        if (b.n_chunks == 0) return;
+        DevBuf<unsigned long long> err(1, s);
+        CUDA_CHECK(cudaMemsetAsync(err.get(), 0xFF, 8, s));
+        unsigned grid = (unsigned)std::min<uint64_t>(b.n_chunks, 1u << 30);
+        IndexView<Suf> v = view();
+        if (mode == 0) {
+            if (brute) CBL_LAUNCH((seq_words_kernel<W, Suf, 0, true>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err.get());
+            else CBL_LAUNCH((seq_words_kernel<W, Suf, 0, false>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err.get());
+        } else {
+            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err.get());
+        }
+        unsigned long long e = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&e, err.get(), 8, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (e != ULLONG_MAX)
+            throw Error(CBL_EINVAL, "non-ACGT byte in sequence near byte offset " + std::to_string(e) +
+                                        " (the GPU path rejects what the reference silently drops; see DESIGN.md)");
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // sort / unique
+    // ------------------------------------------------------------------------------------------
+    // sorts n keys; returns the buffer (a or b) that holds the result
+    W* sort_keys(W* a, W* b, uint64_t n) {
+        if (n <= 1) return a;
+        if (n > RS_MAX_KEYS) throw Error(CBL_EINVAL, "internal: sort batch too large");
+        const int key_bits = P_.bits + P_.pos_bits;
+        const int n_pass = (key_bits + 7) / 8;
+        DevBuf<unsigned long long> hist((size_t)n_pass * 256, st_);
+        hist.zero();
+        unsigned hgrid = (unsigned)std::min<uint64_t>(div_up(n, RS_THREADS * 16), 148 * 8);
+        CBL_LAUNCH((radix_hist_kernel<W>), hgrid, RS_THREADS, 0, st_, a, n, n_pass, hist.get());
+        CBL_LAUNCH(radix_scan_hist_kernel, n_pass, 256, 0, st_, hist.get());
+        const uint64_t tiles = div_up(n, RsTile<W>::TILE);
+        DevBuf<uint32_t> status(tiles * 256, st_), counter(1, st_);
+        const size_t smem = sizeof(W) * RsTile<W>::TILE;
+        W *src = a, *dst = b;
+        for (int p = 0; p < n_pass; p++) {
+            status.zero();
+            counter.zero();
+            CBL_LAUNCH((radix_pass_kernel<W, false>), (unsigned)tiles, RS_THREADS, smem, st_, src, dst, nullptr, nullptr, n, 8 * p,
+                       hist.get() + (size_t)p * 256, status.get(), counter.get());
+            std::swap(src, dst);
+        }
+        return src;
+    }
+    uint64_t read_u64(const unsigned long long* d) {
+        unsigned long long v = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        return v;
+    }
+    uint64_t unique_keys(const W* sorted, uint64_t n, W* out) {
+        if (n == 0) return 0;
+        const uint64_t tiles = div_up(n, OP_TILE);
+        Lookback lb(tiles, st_);
+        DevBuf<unsigned long long> cnt(1, st_);
+        cnt.zero();
+        CBL_LAUNCH((unique_kernel<W>), (unsigned)tiles, OP_THREADS, 0, st_, sorted, n, out, lb.status.get(), lb.counter.get(), cnt.get());
+        return read_u64(cnt.get());
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // mutation: sorted distinct probe keys -> edits -> new directory -> new suffix array
+    // ------------------------------------------------------------------------------------------
+    struct NewState {
+        DevBuf<uint64_t> bitmap;
+        DevBuf<uint32_t> blkrank, bucket_prefix, bucket_off;
+        DevBuf<Suf> suf;
+        uint32_t nb = 0;
+        uint64_t n = 0;
+        uint32_t last_prefix = 0;
+        bool changed = false;
+    };
+    void adopt(NewState& ns) {
+        bitmap_.swap(ns.bitmap); blkrank_.swap(ns.blkrank); bucket_prefix_.swap(ns.bucket_prefix);
+        bucket_off_.swap(ns.bucket_off); suf_.swap(ns.suf);
+        nb_ = ns.nb; n_ = ns.n; last_prefix_ = ns.last_prefix;
+        bitmap_.rebind(st_); blkrank_.rebind(st_); bucket_prefix_.rebind(st_); bucket_off_.rebind(st_); suf_.rebind(st_);
+    }
+
+    // keys: sorted distinct words.  probe_ix: index they are looked up in (own view unless KEEP_ONLY).
+    // scratch_ins: optional buffer (>= nk words) reused for the insert list.
+    void compute_new_state(const W* keys, uint64_t nk, int mode, const IndexView<Suf>& probe_ix, W* scratch_ins, NewState& ns) {
+        ns.changed = false;
+        if (nk == 0) return;
+        const IndexView<Suf> self = view();
+        const uint64_t tiles = div_up(nk, OP_TILE);
+        DevBuf<W> ins_own;
+        W* ins_key = scratch_ins;
+        const bool want_ins = (mode & EDIT_INS) != 0;
+        const bool want_del = (mode & (EDIT_DEL | EDIT_KEEP_ONLY)) != 0;
+        if (want_ins && !ins_key) { ins_own.alloc(nk, st_); ins_key = ins_own.get(); }
+        DevBuf<uint64_t> ins_vpos(want_ins ? nk : 1, st_), del_idx(want_del ? nk : 1, st_);
+        DevBuf<int> delta(nb_ ? nb_ : 1, st_);
+        delta.zero();
+        ns.bitmap.alloc(bitmap_words_, st_);
+        CUDA_CHECK(cudaMemcpyAsync(ns.bitmap.get(), bitmap_.get(), bitmap_words_ * 8, cudaMemcpyDeviceToDevice, st_));
+        Lookback lb_ins(tiles, st_), lb_del(tiles, st_);
+        DevBuf<unsigned long long> counts(4, st_);
+        counts.zero();
+        CBL_LAUNCH((probe_edits_kernel<W, Suf>), (unsigned)tiles, OP_THREADS, 0, st_, keys, nk, probe_ix, self, P_, mode, ins_key,
+                   ins_vpos.get(), del_idx.get(), delta.get(), (unsigned long long*)ns.bitmap.get(), lb_ins.status.get(),
+                   lb_del.status.get(), lb_ins.counter.get(), counts.get());
+        unsigned long long h_counts[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(h_counts, counts.get(), 16, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        const uint64_t ni = h_counts[0], nd = h_counts[1];
+        if (ni == 0 && nd == 0) return;
+        const uint64_t n_new = n_ + ni - nd;
+        if (n_new >= (1ull << 32))
+            throw Error(CBL_EINVAL, "shard would hold >= 2^32 k-mers; bucket offsets are 32-bit — shard the index over more GPUs");
+
+        // directory
+        if (nb_) CBL_LAUNCH(clear_emptied_kernel, (unsigned)div_up(nb_, 256), 256, 0, st_, bucket_prefix_.get(), bucket_off_.get(),
+                            delta.get(), nb_, (unsigned long long*)ns.bitmap.get());
+        ns.blkrank.alloc(n_blocks_, st_);
+        {
+            const uint64_t t = div_up(n_blocks_, OP_TILE);
+            Lookback lb(t, st_);
+            CBL_LAUNCH(rank_directory_kernel, (unsigned)t, OP_THREADS, 0, st_, ns.bitmap.get(), n_blocks_, ns.blkrank.get(),
+                       lb.status.get(), lb.counter.get(), counts.get() + 2);
+        }
+        const uint64_t nb_new = read_u64(counts.get() + 2);
+        DevBuf<uint32_t> size_new(nb_new + 1, st_);
+        size_new.zero();
+        ns.bucket_prefix.alloc(nb_new ? nb_new : 1, st_);
+        if (nb_) CBL_LAUNCH(fill_sizes_old_kernel, (unsigned)div_up(nb_, 256), 256, 0, st_, bucket_prefix_.get(), bucket_off_.get(),
+                            delta.get(), nb_, ns.bitmap.get(), ns.blkrank.get(), size_new.get(), ns.bucket_prefix.get());
+        if (ni) CBL_LAUNCH((fill_sizes_ins_kernel<W>), (unsigned)div_up(ni, 256), 256, 0, st_, ins_key, ni, P_, bitmap_.get(),
+                           ns.bitmap.get(), ns.blkrank.get(), size_new.get(), ns.bucket_prefix.get());
+        ns.bucket_off.alloc(nb_new + 1, st_);
+        {
+            const uint64_t t = div_up(nb_new + 1, OP_TILE);
+            Lookback lb(t, st_);
+            CBL_LAUNCH(scan_sizes_kernel, (unsigned)t, OP_THREADS, 0, st_, size_new.get(), nb_new, ns.bucket_off.get(), lb.status.get(),
+                       lb.counter.get());
+        }
+        // suffixes
+        ns.suf.alloc(n_new ? n_new : 1, st_);
+        {
+            const uint64_t V = n_ + ni;
+            const uint64_t t = div_up(V, OP_TILE);
+            Lookback lb(t, st_);
+            if (t) CBL_LAUNCH((apply_edits_kernel<W, Suf>), (unsigned)t, OP_THREADS, 0, st_, suf_.get(), n_, ins_vpos.get(), ins_key, ni,
+                              del_idx.get(), nd, ns.suf.get(), P_, lb.status.get(), lb.counter.get());
+        }
+        uint32_t tail[2] = {0, 0};  // total from the offsets scan, prefix of the last bucket
+        CUDA_CHECK(cudaMemcpyAsync(&tail[0], ns.bucket_off.get() + nb_new, 4, cudaMemcpyDeviceToHost, st_));
+        if (nb_new) CUDA_CHECK(cudaMemcpyAsync(&tail[1], ns.bucket_prefix.get() + (nb_new - 1), 4, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        if ((uint64_t)tail[0] != n_new)
+            throw Error(CBL_ECUDA, "internal: directory total " + std::to_string(tail[0]) + " != element count " + std::to_string(n_new));
+        ns.nb = (uint32_t)nb_new;
+        ns.n = n_new;
+        ns.last_prefix = tail[1];
+        ns.changed = true;
+    }
+
+    // unsorted words in `a` (n of them, `b` same-size scratch) -> applied to this index
+    void mutate_with_words(W* a, W* b, uint64_t n, int mode) {
+        if (n == 0) return;
+        W* sorted = sort_keys(a, b, n);
+        W* other = sorted == a ? b : a;
+        uint64_t nu = unique_keys(sorted, n, other);
+        NewState ns;
+        compute_new_state(other, nu, mode, view(), sorted, ns);
+        if (ns.changed) adopt(ns);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // sequence front ends
+    // ------------------------------------------------------------------------------------------
+    void mutate_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, int mode) {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        check_records(offsets, n_seqs);
+        PieceList pl;
+        build_pieces(offsets, 0, n_seqs, pl);
+        size_t p = 0;
+        const size_t np = pl.kmers.size();
+        while (p < np) {
+            size_t q = p;
+            uint64_t nk = 0;
+            while (q < np && (q == p || nk + pl.kmers[q] <= batch_kmers_)) { nk += pl.kmers[q]; q++; }
+            DevPieces dp;
+            upload_pieces(pl, p, q, pl.out_off[p], d_seq, n_bytes, dp, st_);
+            DevBuf<W> a(nk, st_), b(nk, st_);
+            run_seq_words(dp.batch, 0, false, a.get(), nullptr, st_);
+            mutate_with_words(a.get(), b.get(), nk, mode);
+            p = q;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    void insert_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs) override {
+        mutate_seqs_dev(d_seq, n_bytes, offsets, n_seqs, EDIT_INS);
+    }
+    void remove_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs) override {
+        mutate_seqs_dev(d_seq, n_bytes, offsets, n_seqs, EDIT_DEL);
+    }
+    void contains_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, uint8_t* d_out) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        check_records(offsets, n_seqs);
+        PieceList pl;
+        build_pieces(offsets, 0, n_seqs, pl);
+        if (pl.kmers.empty()) return;
+        DevPieces dp;
+        upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, st_);
+        run_seq_words(dp.batch, 1, false, nullptr, d_out, st_);
+    }
+    void seq_words_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, void* d_words, bool brute) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        check_records(offsets, n_seqs);
+        PieceList pl;
+        build_pieces(offsets, 0, n_seqs, pl);
+        if (pl.kmers.empty()) return;
+        DevPieces dp;
+        upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, st_);
+        run_seq_words(dp.batch, 0, brute, (W*)d_words, nullptr, st_);
+    }
+
+    // host buffers: records are grouped (~CBL_GROUP_BYTES each) and streamed through the device
+    template <class F> void for_each_group(const uint64_t* offsets, size_t n_seqs, F&& f) const {
+        const uint64_t group_bytes = env_u64("CBL_GROUP_BYTES", 256ull << 20);
+        size_t r = 0;
+        while (r < n_seqs) {
+            size_t q = r;
+            while (q < n_seqs && (q == r || offsets[q + 1] - offsets[r] <= group_bytes)) q++;
+            f(r, q);
+            r = q;
+        }
+    }
+    void insert_seqs(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, bool remove) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        check_records(offsets, n_seqs);
+        for_each_group(offsets, n_seqs, [&](size_t r, size_t q) {
+            const uint64_t b0 = offsets[r], nbytes = offsets[q] - b0;
+            DevBuf<uint8_t> d(nbytes + 64, st_);
+            CUDA_CHECK(cudaMemcpyAsync(d.get(), seq + b0, nbytes, cudaMemcpyHostToDevice, st_));
+            std::vector<uint64_t> off(q - r + 1);
+            for (size_t i = r; i <= q; i++) off[i - r] = offsets[i] - b0;
+            mutate_seqs_dev(d.get(), nbytes, off.data(), q - r, remove ? EDIT_DEL : EDIT_INS);
+        });
+    }
+    void contains_seqs(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint8_t* out) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        check_records(offsets, n_seqs);
+        CUDA_CHECK(cudaStreamSynchronize(st_));  // index state is final before the side streams read it
+        // two side streams alternate so the copies of group g+1 overlap the kernel of group g
+        int slot = 0;
+        uint64_t kmer_base = 0;
+        std::string first_error;
+        int32_t first_code = 0;
+        for_each_group(offsets, n_seqs, [&](size_t r, size_t q) {
+            cudaStream_t s = side_[slot];
+            slot ^= 1;
+            const uint64_t b0 = offsets[r], nbytes = offsets[q] - b0;
+            std::vector<uint64_t> off(q - r + 1);
+            for (size_t i = r; i <= q; i++) off[i - r] = offsets[i] - b0;
+            PieceList pl;
+            build_pieces(off.data(), 0, q - r, pl);
+            DevBuf<uint8_t> d(nbytes + 64, s), flags(pl.n_kmers, s);
+            CUDA_CHECK(cudaMemcpyAsync(d.get(), seq + b0, nbytes, cudaMemcpyHostToDevice, s));
+            DevPieces dp;
+            upload_pieces(pl, 0, pl.kmers.size(), 0, d.get(), nbytes, dp, s);
+            try {
+                run_seq_words(dp.batch, 1, false, nullptr, flags.get(), s);
+            } catch (const Error& e) {
+                if (first_error.empty()) { first_error = e.what(); first_code = e.code; }
+            }
+            CUDA_CHECK(cudaMemcpyAsync(out + kmer_base, flags.get(), pl.n_kmers, cudaMemcpyDeviceToHost, s));
+            kmer_base += pl.n_kmers;
+        });
+        for (auto& s : side_) CUDA_CHECK(cudaStreamSynchronize(s));
+        if (!first_error.empty()) throw Error(first_code, first_error);
+    }
+    void seq_words(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint64_t* lo, uint64_t* hi, bool brute) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        check_records(offsets, n_seqs);
+        const uint64_t nbytes = offsets[n_seqs] - offsets[0];
+        std::vector<uint64_t> off(n_seqs + 1);
+        for (size_t i = 0; i <= n_seqs; i++) off[i] = offsets[i] - offsets[0];
+        uint64_t nk = 0;
+        for (size_t i = 0; i < n_seqs; i++) nk += off[i + 1] - off[i] - cfg_.k + 1;
+        DevBuf<uint8_t> d(nbytes + 64, st_);
+        CUDA_CHECK(cudaMemcpyAsync(d.get(), seq + offsets[0], nbytes, cudaMemcpyHostToDevice, st_));
+        DevBuf<W> w(nk, st_);
+        seq_words_dev(d.get(), nbytes, off.data(), n_seqs, w.get(), brute);
+        download_words(w.get(), nk, lo, hi);
+    }
+    void download_words(const W* d, uint64_t n, uint64_t* lo, uint64_t* hi) {
+        if (n == 0) return;
+        std::vector<W> h(n);
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), d, n * sizeof(W), cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        for (uint64_t i = 0; i < n; i++) {
+            lo[i] = (uint64_t)h[i];
+            if (hi) hi[i] = sizeof(W) == 16 ? (uint64_t)((u128)h[i] >> 64) : 0;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // k-mer / word level operations
+    // ------------------------------------------------------------------------------------------
+    void words_op_dev(int op, const void* d_words, uint64_t n, uint8_t* d_out) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        if (n == 0) return;
+        if (d_out) CBL_LAUNCH((probe_words_kernel<W, Suf>), (unsigned)div_up(n, 256), 256, 0, st_, (const W*)d_words, n, view(), P_, d_out);
+        if (op == 0) return;
+        uint64_t done = 0;
+        while (done < n) {
+            uint64_t m = std::min<uint64_t>(batch_kmers_, n - done);
+            DevBuf<W> a(m, st_), b(m, st_);
+            CUDA_CHECK(cudaMemcpyAsync(a.get(), (const W*)d_words + done, m * sizeof(W), cudaMemcpyDeviceToDevice, st_));
+            mutate_with_words(a.get(), b.get(), m, op == 1 ? EDIT_INS : EDIT_DEL);
+            done += m;
+        }
+    }
+    void kmers_op(int op, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        if (n == 0) return;
+        DevBuf<uint64_t> dlo(n, st_), dhi(hi ? n : 1, st_);
+        CUDA_CHECK(cudaMemcpyAsync(dlo.get(), lo, n * 8, cudaMemcpyHostToDevice, st_));
+        if (hi) CUDA_CHECK(cudaMemcpyAsync(dhi.get(), hi, n * 8, cudaMemcpyHostToDevice, st_));
+        DevBuf<W> w(n, st_);
+        CBL_LAUNCH((kmers_to_words_kernel<W>), (unsigned)div_up(n, 256), 256, 0, st_, dlo.get(), hi ? dhi.get() : nullptr, (uint64_t)n, P_, w.get());
+        DevBuf<uint8_t> flags(n, st_);
+        words_op_dev(op, w.get(), n, out ? flags.get() : nullptr);
+        if (out) CUDA_CHECK(cudaMemcpyAsync(out, flags.get(), n, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    void load_sorted_words(const uint64_t* lo, const uint64_t* hi, uint64_t n) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        if (n == 0) return;
+        std::vector<W> h(n);
+        for (uint64_t i = 0; i < n; i++) h[i] = sizeof(W) == 16 ? (W)(((u128)(hi ? hi[i] : 0) << 64) | lo[i]) : (W)lo[i];
+        DevBuf<W> d(n, st_);
+        CUDA_CHECK(cudaMemcpyAsync(d.get(), h.data(), n * sizeof(W), cudaMemcpyHostToDevice, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        words_op_dev(1, d.get(), n, nullptr);
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // export / iteration (ascending word order == ascending prefix then suffix)
+    // ------------------------------------------------------------------------------------------
+    void export_words_dev(uint64_t start, uint64_t count, int to_kmers, void* d_out) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        if (count == 0) return;
+        if (start + count > n_) throw Error(CBL_EINVAL, "export range out of bounds");
+        CBL_LAUNCH((expand_kernel<W, Suf>), (unsigned)div_up(count, OP_TILE), OP_THREADS, 0, st_, view(), P_, start, count, to_kmers, (W*)d_out);
+    }
+    void export_words(uint64_t start, uint64_t cap, int to_kmers, uint64_t* lo, uint64_t* hi, uint64_t* n_out) override {
+        uint64_t cnt = start >= n_ ? 0 : std::min<uint64_t>(cap, n_ - start);
+        *n_out = cnt;
+        if (!cnt) return;
+        DevBuf<W> d(cnt, st_);
+        export_words_dev(start, cnt, to_kmers, d.get());
+        download_words(d.get(), cnt, lo, hi);
+    }
+    void bucket_sizes(uint32_t* prefixes, uint32_t* sizes, uint64_t cap, uint64_t* n_out) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        *n_out = nb_;
+        if (!prefixes || !nb_) return;
+        if (cap < nb_) throw Error(CBL_EINVAL, "output buffer too small");
+        DevBuf<uint32_t> sz(nb_, st_);
+        CBL_LAUNCH(bucket_sizes_kernel, (unsigned)div_up(nb_, 256), 256, 0, st_, bucket_off_.get(), nb_, sz.get());
+        CUDA_CHECK(cudaMemcpyAsync(prefixes, bucket_prefix_.get(), (size_t)nb_ * 4, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaMemcpyAsync(sizes, sz.get(), (size_t)nb_ * 4, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // set operations (src/cbl.rs:411-569): both operands must agree on every parameter
+    // ------------------------------------------------------------------------------------------
+    Index* check_other(IIndex* o) {
+        auto* p = dynamic_cast<Index*>(o);
+        const Config& c = o->config();
+        if (!p || c.k != cfg_.k || c.prefix_bits != cfg_.prefix_bits || c.word_bits != cfg_.word_bits)
+            throw Error(CBL_EINVAL, "set operation between indexes with different K / T / PREFIX_BITS");
+        if (c.canonical != cfg_.canonical) throw Error(CBL_EINVAL, "One of the index is canonical while the other isn't");  // cbl.rs:422-425
+        if (c.device != cfg_.device) throw Error(CBL_EINVAL, "set operation between indexes on different devices");
+        return p;
+    }
+    void setop_new_state(int op, Index* o, NewState& ns) {
+        o->sync();
+        if (op == SETOP_AND) {
+            if (n_ == 0) { ns.changed = false; return; }
+            DevBuf<W> mine(n_, st_);
+            export_words_dev(0, n_, 0, mine.get());
+            compute_new_state(mine.get(), n_, EDIT_KEEP_ONLY, o->view(), nullptr, ns);
+        } else {
+            if (o->n_ == 0) { ns.changed = false; return; }
+            DevBuf<W> theirs(o->n_, st_);
+            // expand the other operand on OUR stream (its state is final after o->sync())
+            CBL_LAUNCH((expand_kernel<W, Suf>), (unsigned)div_up(o->n_, OP_TILE), OP_THREADS, 0, st_, o->view(), P_, (uint64_t)0, o->n_, 0, theirs.get());
+            const int mode = op == SETOP_OR ? EDIT_INS : op == SETOP_SUB ? EDIT_DEL : (EDIT_INS | EDIT_DEL);
+            compute_new_state(theirs.get(), o->n_, mode, view(), nullptr, ns);
+        }
+    }
+    void setop_assign(int op, IIndex* other) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        Index* o = check_other(other);
+        if (o == this) {  // x op x
+            if (op == SETOP_SUB || op == SETOP_XOR) clear();
+            return;
+        }
+        NewState ns;
+        setop_new_state(op, o, ns);
+        if (ns.changed) adopt(ns);
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    IIndex* setop(int op, IIndex* other) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        Index* o = check_other(other);
+        std::unique_ptr<Index> res(new Index(cfg_));
+        if (o == this) {
+            if (op == SETOP_OR || op == SETOP_AND) { sync(); res->copy_state_from(*this); res->sync(); }
+            return res.release();
+        }
+        NewState ns;
+        setop_new_state(op, o, ns);
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        if (ns.changed) res->adopt(ns);   // buffers were allocated on our stream; work on them is complete
+        else { res->copy_state_from(*this); res->sync(); }
+        return res.release();
+    }
+    void clear() {
+        bitmap_.zero();
+        blkrank_.zero();
+        bucket_off_.alloc(1, st_);
+        bucket_off_.zero();
+        nb_ = 0; n_ = 0; last_prefix_ = 0;
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+};
+
+uint64_t total_kmers_of(const Config& cfg, const uint64_t* offsets, size_t n_seqs) {
+    uint64_t t = 0;
+    for (size_t i = 0; i < n_seqs; i++) {
+        uint64_t len = offsets[i + 1] - offsets[i];
+        if (len >= (uint64_t)cfg.k) t += len - cfg.k + 1;
+    }
+    return t;
+}
+
+IIndex* make_index(const Config& cfg) {
+    // parameter rules of the reference: build.rs:15-53, src/cbl.rs:87-91, src/wordset/mod.rs:37-41
+    if (cfg.k < 1 || cfg.k > 59) throw Error(CBL_EINVAL, "K must be in 1..=59");
+    const int bits = 2 * cfg.k, pb = pos_bits_for(bits), word = bits + pb;
+    if (cfg.word_bits != 32 && cfg.word_bits != 64 && cfg.word_bits != 128) throw Error(CBL_EINVAL, "T must be u32, u64 or u128");
+    if (word > cfg.word_bits)
+        throw Error(CBL_EINVAL, "Cannot fit a " + std::to_string(cfg.k) + "-mer and its length in a " + std::to_string(cfg.word_bits) + "-bit integer");
+    if (cfg.prefix_bits < 1 || cfg.prefix_bits > 31) throw Error(CBL_EINVAL, "PREFIX_BITS should be in 1..=31 on the GPU path (reference: <= 32)");
+    const int sb = word - cfg.prefix_bits;
+    if (sb <= 0) throw Error(CBL_EINVAL, "SUFFIX_BITS should be != 0");
+    if (cfg.canonical && (cfg.k % 2 == 0)) throw Error(CBL_EINVAL, "canonical k-mers need an odd K (build.rs:22)");
+    int ndev = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    if (cfg.device < 0 || cfg.device >= ndev) throw Error(CBL_EINVAL, "no such CUDA device");
+    // device key = smallest of u64 / u128 that holds the word, independent of the host-side T
+    if (word <= 64) {
+        if (sb <= 32) return new Index<uint64_t, uint32_t>(cfg);
+        return new Index<uint64_t, uint64_t>(cfg);
+    }
+    if (sb <= 64) return new Index<u128, uint64_t>(cfg);
+    return new Index<u128, u128>(cfg);
+}
+
+}  // namespace cbl

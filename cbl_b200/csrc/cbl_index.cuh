@@ -1,0 +1,65 @@
+// Host-side orchestration of one device-resident CBL shard (the B200 counterpart of src/cbl.rs).
+// One handle = one CUDA stream; every public operation enqueues its kernels on that stream and
+// returns when the results the caller asked for are on the host.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cbl {
+
+enum SetOp : int { SETOP_OR = 0, SETOP_AND = 1, SETOP_SUB = 2, SETOP_XOR = 3 };
+
+struct Config {
+    int k, word_bits, prefix_bits, canonical, device;
+};
+
+// Records of one batch, already cut into 2048-aligned pieces (host arrays).
+struct PieceList {
+    std::vector<uint64_t> byte_off, out_off, chunk0;
+    std::vector<uint32_t> kmers;
+    uint64_t n_kmers = 0, n_chunks = 0;
+};
+
+class IIndex {
+public:
+    virtual ~IIndex() {}
+    virtual const Config& config() const = 0;
+    virtual const KParams& params() const = 0;
+    virtual cudaStream_t stream() const = 0;
+    virtual uint64_t count() const = 0;
+    virtual uint32_t n_buckets() const = 0;
+    virtual bool is_empty_reference_semantics() const = 0;
+    virtual IIndex* clone() = 0;
+    // sequences: `d_seq` device pointer to n_bytes bytes, host offsets[n_seqs + 1]
+    virtual void insert_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs) = 0;
+    virtual void remove_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs) = 0;
+    virtual void contains_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, uint8_t* d_out) = 0;
+    virtual void seq_words_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, void* d_words, bool brute) = 0;
+    // host-buffer front ends (copies inside)
+    virtual void insert_seqs(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, bool remove) = 0;
+    virtual void contains_seqs(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint8_t* out) = 0;
+    virtual void seq_words(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint64_t* lo, uint64_t* hi, bool brute) = 0;
+    // k-mer integers
+    virtual void kmers_op(int op /*0 contains,1 insert,2 remove*/, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out) = 0;
+    // words (already transformed) — used by the sharded multi-GPU path after the all-to-all
+    virtual void words_op_dev(int op, const void* d_words, uint64_t n, uint8_t* d_out) = 0;
+    // set operations
+    virtual IIndex* setop(int op, IIndex* other) = 0;
+    virtual void setop_assign(int op, IIndex* other) = 0;
+    // export
+    virtual void export_words(uint64_t start, uint64_t cap, int to_kmers, uint64_t* lo, uint64_t* hi, uint64_t* n_out) = 0;
+    virtual void export_words_dev(uint64_t start, uint64_t count, int to_kmers, void* d_out) = 0;
+    virtual void bucket_sizes(uint32_t* prefixes, uint32_t* sizes, uint64_t cap, uint64_t* n_out) = 0;
+    virtual void load_sorted_words(const uint64_t* lo, const uint64_t* hi, uint64_t n) = 0;
+    virtual void sync() = 0;
+    std::string last_error;
+};
+
+IIndex* make_index(const Config& cfg);
+std::string prof_report();
+uint64_t total_kmers_of(const Config& cfg, const uint64_t* offsets, size_t n_seqs);
+
+}  // namespace cbl

@@ -1,0 +1,89 @@
+// Host-side plumbing shared by the .cu files: error handling that never lets an exception cross the
+// C ABI, a stream-ordered device buffer, and the kernel-launch counter bench.py reports.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <utility>
+
+#include "../../include/cbl_gpu.h"  // status codes
+#include "kmer_necklace.cuh"
+
+namespace cbl {
+
+struct Error : std::runtime_error {
+    int32_t code;
+    Error(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(e), what, file, line, cudaGetErrorString(e));
+        throw Error(e == cudaErrorMemoryAllocation ? CBL_ENOMEM : CBL_ECUDA, buf);
+    }
+}
+#define CUDA_CHECK(x) ::cbl::cuda_check((x), #x, __FILE__, __LINE__)
+
+extern std::atomic<uint64_t> g_launches;  // every kernel launched by this library
+
+// Optional per-kernel device timing (CUDA events on the launching stream), off by default.
+// bench.py turns it on for a separate, untimed pass to attribute time to kernels.
+struct ProfRec { const char* tag; cudaEvent_t a, b; };
+extern std::atomic<int> g_prof_on;
+void prof_push(const char* tag, cudaEvent_t a, cudaEvent_t b);
+
+#define CBL_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+    do {                                                                   \
+        cudaEvent_t _e0 = nullptr, _e1 = nullptr;                          \
+        const bool _prof = ::cbl::g_prof_on.load(std::memory_order_relaxed) != 0; \
+        if (_prof) { cudaEventCreate(&_e0); cudaEventCreate(&_e1); cudaEventRecord(_e0, (stream)); } \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
+        if (_prof) { cudaEventRecord(_e1, (stream)); ::cbl::prof_push(#kernel, _e0, _e1); } \
+        ::cbl::g_launches.fetch_add(1, std::memory_order_relaxed);         \
+        CUDA_CHECK(cudaGetLastError());                                    \
+    } while (0)
+
+// Stream-ordered device allocation (cudaMallocAsync pool: frees are cached, no device sync).
+template <class T>
+class DevBuf {
+    T* p_ = nullptr;
+    size_t n_ = 0;
+    cudaStream_t s_ = nullptr;
+
+public:
+    DevBuf() = default;
+    DevBuf(size_t n, cudaStream_t s) { alloc(n, s); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p_(o.p_), n_(o.n_), s_(o.s_) { o.p_ = nullptr; o.n_ = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p_ = o.p_; n_ = o.n_; s_ = o.s_; o.p_ = nullptr; o.n_ = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t n, cudaStream_t s) {
+        release();
+        s_ = s;
+        n_ = n;
+        size_t bytes = (n ? n : 1) * sizeof(T);
+        CUDA_CHECK(cudaMallocAsync((void**)&p_, bytes, s));
+    }
+    void release() {
+        if (p_) { cudaFreeAsync(p_, s_); p_ = nullptr; n_ = 0; }
+    }
+    void zero() { if (p_) CUDA_CHECK(cudaMemsetAsync(p_, 0, (n_ ? n_ : 1) * sizeof(T), s_)); }
+    T* get() const { return p_; }
+    size_t size() const { return n_; }
+    size_t bytes() const { return n_ * sizeof(T); }
+    void rebind(cudaStream_t s) { s_ = s; }  // later frees are ordered on `s` (all prior work must be complete)
+    void swap(DevBuf& o) { std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(s_, o.s_); }
+};
+
+CBL_HD uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+}  // namespace cbl

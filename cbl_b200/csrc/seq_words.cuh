@@ -1,0 +1,172 @@
+// Kernel k1+k2: reads -> 2-bit packed windows -> (canonical) -> necklace -> word, fused (optionally)
+// with the membership probe.  Replaces src/kmer.rs (from_nucs/append/canonical) + src/necklace/queue.rs
+// + CBL::get_seq_words / get_seq_chunks (src/cbl.rs:239-289) for a whole batch of records.
+//
+// Work decomposition mirrors the reference's own chunking so that results come out in ITS order:
+// one CTA (2 warps) per 2048-k-mer chunk of a "piece" (a record, or a 2048-aligned slice of a long
+// record).  Inside a warp every lane packs 32 bases (two/three aligned 16-byte loads + funnel shifts)
+// into one 64-bit word; iteration j broadcasts words j, j+1(, j+2) by warp shuffle and lane l cuts
+// the window starting at base 32j + l out of them, so global stores are fully coalesced (lane l
+// writes k-mer 32j + l).  Canonical mode reproduces the per-chunk "forward words first, then the
+// reverse-complemented ones" order of src/cbl.rs:248-275 with ballot prefix counts.
+#pragma once
+#include "index_view.cuh"
+
+namespace cbl {
+
+constexpr int CHUNK_KMERS = 2048;  // src/cbl.rs:67 CHUNK_SIZE
+constexpr int SW_THREADS = 64;
+
+struct SeqBatch {
+    const uint8_t* seq;          // concatenated record bytes (device)
+    const uint8_t* seq_end;      // one past the last readable byte
+    const uint64_t* piece_byte;  // [n_pieces]   first byte of the piece
+    const uint64_t* piece_out;   // [n_pieces]   output slot of the piece's first k-mer
+    const uint32_t* piece_kmers; // [n_pieces]   number of k-mers in the piece
+    const uint64_t* piece_chunk0;// [n_pieces+1] prefix sum of chunks per piece
+    uint32_t n_pieces;
+    uint64_t n_chunks;
+};
+
+// 32 bases starting at p (any alignment) -> one 64-bit word, first base most significant.
+// Only bytes below `nvalid` are validated (and must be readable below `end`); the rest read as 'A'.
+__device__ __forceinline__ uint64_t load_pack32(const uint8_t* p, const uint8_t* end, int nvalid, bool& bad) {
+    if (nvalid <= 0) return 0;
+    const uintptr_t a = (uintptr_t)p;
+    const uint4* a0 = (const uint4*)(a & ~(uintptr_t)15);
+    const int sh = (int)(a & 15);
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
+    v0 = __ldg(a0);  // contains p itself, which is readable since nvalid > 0
+    if ((const uint8_t*)(a0 + 1) < end) v1 = __ldg(a0 + 1);
+    if (sh != 0 && (const uint8_t*)(a0 + 2) < end) v2 = __ldg(a0 + 2);
+    uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+    const int wo = sh >> 2, bs = (sh & 3) * 8;
+    uint32_t x[8];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        if (wo == c) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j] = __funnelshift_r(w[c + j], w[c + j + 1], bs);
+        }
+    }
+    uint64_t packed = 0;
+    uint32_t badbits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int nb = nvalid - 4 * j;
+        uint32_t rmask = nb >= 4 ? 0xFFFFFFFFu : nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u);
+        uint32_t u = x[j] & 0xDFDFDFDFu;
+        uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+        badbits |= ~ok & rmask;
+        uint32_t xv = (x[j] & rmask) | (0x41414141u & ~rmask);  // out-of-range bytes read as 'A'
+        packed |= (uint64_t)pack4(xv) << (56 - 8 * j);
+    }
+    if (badbits) bad = true;
+    return packed;
+}
+
+template <class W> __device__ __forceinline__ W cut_window(uint64_t A, uint64_t B, uint64_t C, int sh2, int bits);
+template <> __device__ __forceinline__ uint64_t cut_window<uint64_t>(uint64_t A, uint64_t B, uint64_t, int sh2, int bits) {
+    uint64_t v = sh2 ? ((A << sh2) | (B >> (64 - sh2))) : A;
+    return v >> (64 - bits);
+}
+template <> __device__ __forceinline__ u128 cut_window<u128>(uint64_t A, uint64_t B, uint64_t C, int sh2, int bits) {
+    uint64_t hi = sh2 ? ((A << sh2) | (B >> (64 - sh2))) : A;
+    uint64_t lo = sh2 ? ((B << sh2) | (C >> (64 - sh2))) : B;
+    u128 v = ((u128)hi << 64) | lo;
+    return v >> (128 - bits);
+}
+
+// MODE 0: write words (W) to out_words.   MODE 1: probe the index, write one byte per k-mer.
+// BRUTE: use the normative brute-force necklace instead of the fast one (debug / cross-check).
+template <class W, class Suf, int MODE, bool BRUTE>
+__global__ void __launch_bounds__(SW_THREADS) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
+                                                               uint8_t* __restrict__ out_flags, IndexView<Suf> ix,
+                                                               unsigned long long* __restrict__ err_pos) {
+    __shared__ uint32_t s_fwd[2][32];
+    __shared__ uint32_t s_piece;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t chunk = blockIdx.x; chunk < b.n_chunks; chunk += gridDim.x) {
+        if (threadIdx.x == 0) s_piece = (uint32_t)(upper_bound_dev<uint64_t>(b.piece_chunk0, (uint64_t)b.n_pieces + 1, chunk) - 1);
+        __syncthreads();
+        const uint32_t piece = s_piece;
+        const uint64_t ci = chunk - b.piece_chunk0[piece];
+        const uint32_t pk = b.piece_kmers[piece];
+        const uint32_t ks = (uint32_t)(ci * CHUNK_KMERS);
+        const int m = (int)min((uint32_t)CHUNK_KMERS, pk - ks);           // k-mers in this chunk
+        const uint8_t* cbase = b.seq + b.piece_byte[piece] + ks;          // first byte of the chunk
+        const int nbytes = m + P.k - 1;                                   // bytes the chunk may read
+        W* ow = MODE == 0 ? out_words + b.piece_out[piece] + ks : nullptr;
+        uint8_t* of = MODE == 1 ? out_flags + b.piece_out[piece] + ks : nullptr;
+
+        // pack: lane l holds bases [1024*warp + 32*l, +32); lanes 0,1 also hold the two halo words
+        bool bad = false;
+        const int off = 1024 * warp + 32 * lane;
+        uint64_t Wd = load_pack32(cbase + off, b.seq_end, min(32, nbytes - off), bad);
+        uint64_t H = 0;
+        if (lane < 2) {
+            const int hoff = 1024 * warp + 1024 + 32 * lane;
+            H = load_pack32(cbase + hoff, b.seq_end, min(32, nbytes - hoff), bad);
+        }
+        if (bad) atomicMin(err_pos, (unsigned long long)(b.piece_byte[piece] + ks + off));
+
+        const int kbase = 1024 * warp;
+        uint32_t fwd_before = 0, nfwd_total = 0;
+        if (P.canonical) {
+            // pass 1: parity of every window -> ballots, so output slots are known up front
+            for (int j = 0; j < 32; j++) {
+                uint64_t A = __shfl_sync(0xffffffffu, Wd, j);
+                uint64_t B = __shfl_sync(0xffffffffu, (j + 1 < 32) ? Wd : H, (j + 1) & 31);
+                uint64_t C = __shfl_sync(0xffffffffu, (j + 2 < 32) ? Wd : H, (j + 2) & 31);
+                W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
+                bool active = kbase + 32 * j + lane < m;
+                uint32_t bal = __ballot_sync(0xffffffffu, active && !(popc_w(x) & 1));
+                if (lane == 0) s_fwd[warp][j] = bal;
+            }
+            __syncthreads();
+            uint32_t c0 = __popc(s_fwd[0][lane]), c1 = __popc(s_fwd[1][lane]);
+            c0 = warp_sum(c0);
+            c1 = warp_sum(c1);
+            nfwd_total = c0 + c1;
+            fwd_before = warp == 0 ? 0 : c0;
+        }
+        for (int j = 0; j < 32; j++) {
+            if (kbase + 32 * j >= m) break;  // warp-uniform
+            uint64_t A = __shfl_sync(0xffffffffu, Wd, j);
+            uint64_t B = __shfl_sync(0xffffffffu, (j + 1 < 32) ? Wd : H, (j + 1) & 31);
+            uint64_t C = __shfl_sync(0xffffffffu, (j + 2 < 32) ? Wd : H, (j + 2) & 31);
+            const int kidx = kbase + 32 * j + lane;
+            const bool active = kidx < m;
+            W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
+            uint32_t slot = (uint32_t)kidx;
+            if (P.canonical) {
+                const uint32_t bal = s_fwd[warp][j];
+                const uint32_t fb = fwd_before + __popc(bal & lanemask_lt());
+                const bool is_fwd = (bal >> lane) & 1;
+                slot = is_fwd ? fb : nfwd_total + ((uint32_t)kidx - fb);
+                fwd_before += __popc(bal);
+            }
+            if (active) {
+                W word = kmer_to_word<W>(x, P, BRUTE);
+                if (MODE == 0) ow[slot] = word;
+                else of[slot] = probe_key<W, Suf>(ix, P, word).found ? 1 : 0;
+            }
+        }
+        __syncthreads();  // s_piece / s_fwd reuse in the next grid-stride iteration
+    }
+}
+
+// k-mer integers (lo/hi arrays) -> words; single-k-mer API (src/cbl.rs:199-235)
+template <class W>
+__global__ void kmers_to_words_kernel(const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint64_t n, KParams P,
+                                      W* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    W x;
+    if (sizeof(W) == 8) x = (W)lo[i];
+    else x = (W)(((u128)(hi ? hi[i] : 0) << 64) | lo[i]);
+    x &= low_mask<W>(P.bits);
+    out[i] = kmer_to_word<W>(x, P);
+}
+
+}  // namespace cbl

@@ -1,0 +1,129 @@
+/*
+ * cbl_gpu.h — C ABI of libcbl_gpu: a device-resident CBL k-mer set on NVIDIA B200 (sm_100a).
+ *
+ * This boundary REPLACES the reference's Rust->C++ FFI, src/ffi.rs:7-20 (autocxx bindings of
+ * cxx/rank_bv.h `RankBV` and cxx/tiered_vec.h `TieredVec32`, called per prefix group / per element
+ * from src/bitvector/mod.rs:18-62 and src/wordset/mod.rs:87-237).  Per-element calls into a GPU are
+ * a non-starter, so the boundary moves UP to one call per sequence / batch / set operation — the
+ * granularity of the public methods of `CBL<K, T, PREFIX_BITS>` in src/cbl.rs.  Each entry point
+ * names the reference method it serves.  INTEGRATION.md shows the Rust `extern "C"` block and shim.
+ *
+ * Conventions
+ *   - every function returns int32_t status (CBL_OK == 0); no exception or unwind crosses the ABI;
+ *     cbl_last_error(h) / cbl_last_global_error() give the message (the reference panics instead:
+ *     src/cbl.rs:87-91,294-299,422-425 — a host shim turns non-zero statuses into those panics);
+ *   - handles are opaque, created/destroyed only by the library; buffers are caller-owned, plain
+ *     host memory unless the name ends in _dev (then: device pointers on the handle's GPU), and are
+ *     never retained after the call returns;
+ *   - one handle is externally synchronised (like `&mut self`); distinct handles may be used from
+ *     distinct threads;
+ *   - k-mers and words cross as two parallel arrays (lo, hi) of 64-bit halves; hi may be NULL when
+ *     the value fits 64 bits;
+ *   - sequences are raw nucleotide bytes (what needletail hands to the reference), batches are a
+ *     concatenation + n_seqs+1 byte offsets.  A record shorter than K => CBL_EINVAL (the reference
+ *     panics).  Non-ACGT bytes => CBL_EINVAL (the reference silently drops them).
+ */
+#ifndef CBL_GPU_H
+#define CBL_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cbl_handle cbl_t;
+
+enum { CBL_OK = 0, CBL_EINVAL = 1, CBL_ECUDA = 2, CBL_ENOMEM = 3, CBL_ENCCL = 4, CBL_EIO = 5 };
+enum { CBL_OP_OR = 0, CBL_OP_AND = 1, CBL_OP_SUB = 2, CBL_OP_XOR = 3 };
+
+/* ---- life cycle: CBL::new / new_canonical (src/cbl.rs:71-79), Clone, Drop ------------------- */
+/* k: K; word_bits: bits of T (32/64/128, checked like src/cbl.rs:87-91); prefix_bits: PREFIX_BITS */
+int32_t cbl_create(uint32_t k, uint32_t word_bits, uint32_t prefix_bits, int32_t canonical, int32_t device, cbl_t** out);
+int32_t cbl_destroy(cbl_t* h);
+int32_t cbl_clone(cbl_t* h, cbl_t** out);
+const char* cbl_last_error(const cbl_t* h);
+const char* cbl_last_global_error(void);
+
+/* ---- scalar queries: count / is_empty / is_canonical (src/cbl.rs:162-177) ------------------- */
+int32_t cbl_count(const cbl_t* h, uint64_t* out);
+int32_t cbl_is_empty(const cbl_t* h, int32_t* out);   /* reference semantics incl. the all-ones-prefix quirk */
+int32_t cbl_is_canonical(const cbl_t* h, int32_t* out);
+int32_t cbl_num_buckets(const cbl_t* h, uint64_t* out);
+
+/* ---- one sequence: insert_seq / remove_seq / contains_seq / contains_all (src/cbl.rs:293-354) */
+int32_t cbl_insert_seq(cbl_t* h, const uint8_t* seq, size_t len);
+int32_t cbl_remove_seq(cbl_t* h, const uint8_t* seq, size_t len);
+/* out: len-K+1 bytes (0/1) in the reference's order (canonical mode: per 2048-k-mer chunk the
+ * forward-canonical k-mers first, then the reverse-complemented ones; src/cbl.rs:248-275) */
+int32_t cbl_contains_seq(cbl_t* h, const uint8_t* seq, size_t len, uint8_t* out, size_t* n_out);
+int32_t cbl_contains_all(cbl_t* h, const uint8_t* seq, size_t len, int32_t* out);
+
+/* ---- batches of records (the CLI loops `for record { insert_seq(record) }`, examples/cbl.rs:160-163,
+ *      216-228; one call here processes the whole loop) ------------------------------------- */
+int32_t cbl_insert_seqs(cbl_t* h, const uint8_t* buf, const uint64_t* offsets, size_t n_seqs);
+int32_t cbl_remove_seqs(cbl_t* h, const uint8_t* buf, const uint64_t* offsets, size_t n_seqs);
+int32_t cbl_contains_seqs(cbl_t* h, const uint8_t* buf, const uint64_t* offsets, size_t n_seqs, uint8_t* out);
+/* same, with the bytes (and answers) already resident in the handle's GPU memory; offsets on the host */
+int32_t cbl_insert_seqs_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs);
+int32_t cbl_remove_seqs_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs);
+int32_t cbl_contains_seqs_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, uint8_t* d_out);
+/* number of k-mers (= answers) the records yield */
+int32_t cbl_count_kmers(const cbl_t* h, const uint64_t* offsets, size_t n_seqs, uint64_t* out);
+
+/* ---- single k-mers: contains / insert / remove (src/cbl.rs:219-235), batched.  k-mers are IntKmer
+ *      integers (first base most significant, A=0 C=1 T=2 G=3).  out[i] (may be NULL) = whether
+ *      k-mer i was in the set BEFORE the call (insert() returns !out, remove() returns out) ------- */
+int32_t cbl_contains_kmers(cbl_t* h, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out);
+int32_t cbl_insert_kmers(cbl_t* h, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out);
+int32_t cbl_remove_kmers(cbl_t* h, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out);
+
+/* ---- set operations: | & - ^ and |= &= -= ^= (src/cbl.rs:411-569), merge / intersect (:108-124) */
+int32_t cbl_setop(int32_t op, cbl_t* a, cbl_t* b, cbl_t** out);
+int32_t cbl_setop_assign(int32_t op, cbl_t* a, cbl_t* b);
+int32_t cbl_merge_many(cbl_t** hs, size_t n, cbl_t** out);
+int32_t cbl_intersect_many(cbl_t** hs, size_t n, cbl_t** out);
+
+/* ---- iteration: CBL::iter (src/cbl.rs:358-360) in ascending word order; start = element rank --- */
+int32_t cbl_export_words(cbl_t* h, uint64_t start, uint64_t* lo, uint64_t* hi, size_t cap, size_t* n_out);
+int32_t cbl_export_kmers(cbl_t* h, uint64_t start, uint64_t* lo, uint64_t* hi, size_t cap, size_t* n_out);
+/* stats: buckets_sizes (src/cbl.rs:370-372): pass NULL arrays to query the bucket count */
+int32_t cbl_bucket_sizes(cbl_t* h, uint32_t* prefixes, uint32_t* sizes, size_t cap, size_t* n_out);
+
+/* ---- serde: save_to_file / load_from_file (src/cbl.rs:127-160), the reference's bincode varint
+ *      layout (always written with sorted Vec buckets; both bucket variants are read) ------------- */
+int32_t cbl_serialize_size(cbl_t* h, size_t* out);
+int32_t cbl_serialize(cbl_t* h, uint8_t* out, size_t cap, size_t* n_out);
+/* proto supplies K / T / PREFIX_BITS / device (the reference fixes them at compile time) */
+int32_t cbl_deserialize(const cbl_t* proto, const uint8_t* data, size_t len, cbl_t** out);
+int32_t cbl_save_to_file(cbl_t* h, const char* path);
+int32_t cbl_load_from_file(const cbl_t* proto, const char* path, cbl_t** out);
+
+/* ---- sharded (one process per GPU) building blocks: word-level entry points used after the
+ *      all-to-all that routes each word to the GPU owning its prefix range ----------- */
+/* words of the records, in the reference's order, left on the device: d_words = n_kmers * (8|16) bytes */
+int32_t cbl_seq_words_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, void* d_words);
+/* op: 0 contains (d_out required), 1 insert, 2 remove (d_out optional = membership before the call) */
+int32_t cbl_words_op_dev(cbl_t* h, int32_t op, const void* d_words, size_t n, uint8_t* d_out);
+int32_t cbl_export_words_dev(cbl_t* h, uint64_t start, uint64_t count, void* d_out);
+int32_t cbl_word_bytes(const cbl_t* h, int32_t* out);      /* 8 or 16: size of one device word */
+int32_t cbl_suffix_bits(const cbl_t* h, int32_t* out);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+/* words of the records on the host (same order as cbl_seq_words_dev); brute != 0 uses the normative
+ * brute-force necklace instead of the fast path */
+int32_t cbl_seq_words(cbl_t* h, const uint8_t* buf, const uint64_t* offsets, size_t n_seqs, uint64_t* lo, uint64_t* hi, int32_t brute);
+int32_t cbl_sync(cbl_t* h);
+void* cbl_stream(const cbl_t* h);             /* the handle's cudaStream_t */
+uint64_t cbl_launch_count(void);              /* kernels launched by this library so far */
+const char* cbl_build_info(void);
+/* per-kernel device time (CUDA events around every launch); off by default.  report: JSON text
+ * {"kernel": {"n": launches, "ms": total}, ...}, clears the accumulated records */
+void cbl_profile_enable(int32_t on);
+int32_t cbl_profile_report(char* out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBL_GPU_H */
