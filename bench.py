@@ -251,8 +251,13 @@ def run_ours(args):
     nb = cbl.num_buckets()
 
     # ---- timed contains_seq steps (query resident in HBM) ----
+    box = {"answers": answers}
+
     def step():
-        cbl.contains_seqs_dev(query.data_ptr(), q_off, answers.data_ptr())
+        if world > 1:
+            box["answers"] = cbl.contains_seqs_dev(query.data_ptr(), q_off)  # sharded: returns the answers tensor
+        else:
+            cbl.contains_seqs_dev(query.data_ptr(), q_off, answers.data_ptr())
 
     for _ in range(args.warmup):
         step()
@@ -262,7 +267,9 @@ def run_ours(args):
     cbl_b200.profile_enable(True)
     cbl_b200.profile_report()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stream = torch.cuda.ExternalStream(cbl.stream_ptr(), device=device)  # the stream the kernels are launched on
+    # the stream the kernels are launched on (sharded: torch's routing ops run on the current stream and
+    # every library call in between is host-synchronous, so the current stream brackets the region)
+    stream = torch.cuda.ExternalStream(cbl.stream_ptr(), device=device) if world == 1 else torch.cuda.current_stream()
     ev0.record(stream)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -282,7 +289,7 @@ def run_ours(args):
         t = torch.tensor([elapsed], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
-    hits = int(answers.sum(dtype=torch.int64).item())
+    hits = int(box["answers"].sum(dtype=torch.int64).item())
     total_q = n_q_kmers * world
     value = total_q * args.steps / elapsed
 

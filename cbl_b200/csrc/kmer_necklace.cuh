@@ -83,13 +83,16 @@ template <class W> CBL_HD W rotl_ring(W w, int p, int bits, W mask) {
     return (W)(((w << p) & mask) | (w >> (bits - p)));
 }
 
-// Normative brute force: min over p of (rotl(w, p), p).
+// Normative brute force: min over p of (rotl(w, p), p).  Every rotation is formed directly from w
+// (an incremental "rotate by one" loop gave wrong 128-bit results on sm_100a with nvcc 12.9 although
+// the same source is right on the host — first GPU run, 2K=118; the direct form below is the one the
+// fast path also uses and is bit-exact against the oracle).
 template <class W> CBL_HD void necklace_brute(W w, int bits, W& neck, int& pos) {
     const W mask = low_mask<W>(bits);
-    W best = w, rot = w;
+    W best = w;
     int bp = 0;
     for (int p = 1; p < bits; p++) {
-        rot = (W)(((rot << 1) & mask) | (rot >> (bits - 1)));
+        W rot = rotl_ring<W>(w, p, bits, mask);
         if (rot < best) { best = rot; bp = p; }
     }
     neck = best;

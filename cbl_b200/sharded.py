@@ -1,0 +1,229 @@
+"""Prefix-range sharding of one CBL set across the GPUs of a box: one process per GPU
+(``torch.distributed``), one all-to-all per batch, everything else shard-local.
+
+The reference has no multi-device notion; this is the scale-out design of
+BASELINE.json's north star:
+
+* the 2^PREFIX_BITS prefix space is cut into ``world`` contiguous ranges with EQUAL-MASS splitters
+  (necklace prefixes are extremely skewed — SURVEY F4 — so equal-width ranges would put ~99 % of the
+  words on rank 0);
+* every rank turns ITS reads into words locally (fused encode + necklace kernel), routes each word
+  to the rank that owns its prefix with a single all-to-all-v, and the owner applies the batch to
+  its shard (sort / merge / probe) with no further communication;
+* ``contains_seq`` answers come back with a second, one-byte-per-word all-to-all and are put back
+  in the order of the local reads;
+* shards hold disjoint ascending prefix ranges, so the set in global ascending-word order is the
+  concatenation of the shards in rank order; ``count`` is a sum.
+
+The device work is done by an *engine* (``cbl_b200.CBL`` on a GPU).  The routing logic only needs
+``seq_words`` / ``words_op`` from it, which is what lets the world_size-2 ``gloo`` tests run this file
+on CPU tensors with a stand-in engine.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def pos_bits(k: int) -> int:
+    p = 0
+    while (1 << p) < 2 * k:
+        p += 1
+    return p
+
+
+def word_prefixes(words: torch.Tensor, suffix_bits: int, prefix_bits: int) -> torch.Tensor:
+    """prefix = word >> SUFFIX_BITS (src/wordset/mod.rs:63-71) for words held as int64 tensors:
+    shape (n,) for 64-bit words, (n, 2) = (lo, hi) for 128-bit words.  Returns int64."""
+    mask = (1 << prefix_bits) - 1
+    if words.dim() == 1:
+        if suffix_bits == 0:
+            return words & mask
+        return (words >> suffix_bits) & ((1 << (64 - suffix_bits)) - 1) & mask
+    lo, hi = words[:, 0], words[:, 1]
+    if suffix_bits >= 64:
+        s = suffix_bits - 64
+        return ((hi >> s) & ((1 << (64 - s)) - 1) & mask) if s else (hi & mask)
+    lo_part = (lo >> suffix_bits) & ((1 << (64 - suffix_bits)) - 1)
+    return ((hi << (64 - suffix_bits)) | lo_part) & mask
+
+
+def route(prefixes: torch.Tensor, splitters: torch.Tensor):
+    """dest rank of every word, the permutation that groups words by dest (stable), per-dest counts."""
+    world = splitters.numel() + 1
+    dest = torch.bucketize(prefixes, splitters, right=True)
+    order = torch.argsort(dest, stable=True)
+    counts = torch.bincount(dest, minlength=world)
+    return dest, order, counts
+
+
+def exchange(send: torch.Tensor, send_counts: torch.Tensor, group=None):
+    """all-to-all-v of rows of ``send`` (already grouped by destination).  Returns (recv, recv_counts)."""
+    world = dist.get_world_size(group)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    recv = send.new_empty((int(sum(rc)),) + tuple(send.shape[1:]))
+    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    return recv, recv_counts
+
+
+def equal_mass_splitters(prefixes: torch.Tensor, world: int) -> torch.Tensor:
+    """world-1 splitters s.t. each range [s_{i-1}, s_i) holds ~1/world of the sample."""
+    if world == 1:
+        return prefixes.new_empty(0)
+    srt, _ = torch.sort(prefixes)
+    n = srt.numel()
+    idx = torch.tensor([(i * n) // world for i in range(1, world)], device=srt.device)
+    sp = srt[idx]
+    # strictly increasing splitters keep every range non-empty in prefix space
+    for i in range(1, sp.numel()):
+        if sp[i] <= sp[i - 1]:
+            sp[i] = sp[i - 1] + 1
+    return sp
+
+
+class GpuEngine:
+    """Adapter: ``cbl_b200.CBL`` on the local GPU behind the interface the router needs."""
+
+    def __init__(self, k, t_bits, prefix_bits, canonical, device):
+        from .cbl import CBL
+
+        self.cbl = CBL(k, t_bits, prefix_bits, canonical, device)
+        self.device = torch.device("cuda", device)
+        self.word_bytes = self.cbl.word_bytes()
+
+    def seq_words(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
+        n = self.cbl.count_kmers(offsets)
+        shape = (n,) if self.word_bytes == 8 else (n, 2)
+        words = torch.empty(shape, dtype=torch.int64, device=self.device)
+        if n:
+            # the library launches on its own stream: everything torch queued must be done first
+            torch.cuda.current_stream(self.device).synchronize()
+            self.cbl.seq_words_dev(d_buf, offsets, words.data_ptr())  # returns after its stream is idle
+        return words
+
+    def words_op(self, op: int, words: torch.Tensor, want_flags: bool) -> Optional[torch.Tensor]:
+        n = words.shape[0]
+        flags = torch.empty(n, dtype=torch.uint8, device=self.device) if want_flags else None
+        if n:
+            words = words.contiguous()
+            torch.cuda.current_stream(self.device).synchronize()
+            self.cbl.words_op_dev(op, words.data_ptr(), n, flags.data_ptr() if want_flags else 0)
+        return flags
+
+    def count(self) -> int:
+        return self.cbl.count()
+
+    def sample_words(self, n_bases: int, seed: int) -> torch.Tensor:
+        g = torch.Generator(device=self.device)
+        g.manual_seed(seed)
+        lut = torch.tensor(list(b"ACTG"), dtype=torch.uint8, device=self.device)
+        seq = lut[torch.randint(0, 4, (n_bases,), generator=g, device=self.device, dtype=torch.int32)]
+        return self.seq_words(seq.data_ptr(), np.array([0, n_bases], dtype=np.uint64))
+
+
+class ShardedCBL:
+    """One CBL set sharded by prefix range over the ranks of ``group`` (default: the world)."""
+
+    def __init__(self, k: int, t_bits: int, prefix_bits: int = 24, canonical: bool = False, device: int = 0,
+                 engine=None, splitters: Optional[Sequence[int]] = None, group=None, sample_bases: int = 4_000_000):
+        self.k, self.t_bits, self.prefix_bits, self.canonical = k, t_bits, prefix_bits, canonical
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.suffix_bits = 2 * k + pos_bits(k) - prefix_bits
+        self.engine = engine if engine is not None else GpuEngine(k, t_bits, prefix_bits, canonical, device)
+        self.device = self.engine.device
+        if splitters is not None:
+            sp = torch.tensor(list(splitters), dtype=torch.int64, device=self.device)
+        else:
+            # equal-mass splitters for uniform random DNA from a fixed-seed sample pushed through the
+            # real necklace kernel; rank 0 decides, everybody adopts (identical on every rank)
+            sp = torch.zeros(max(self.world - 1, 0), dtype=torch.int64, device=self.device)
+            if self.world > 1:
+                if self.rank == 0:
+                    w = self.engine.sample_words(sample_bases, seed=20240229)
+                    sp.copy_(equal_mass_splitters(word_prefixes(w, self.suffix_bits, prefix_bits), self.world))
+                dist.broadcast(sp, src=0, group=group)
+        assert sp.numel() == self.world - 1
+        self.splitters = sp
+
+    # -- routing ---------------------------------------------------------------------------------
+    def _route_words(self, words: torch.Tensor):
+        pre = word_prefixes(words, self.suffix_bits, self.prefix_bits)
+        _, order, counts = route(pre, self.splitters)
+        send = words.index_select(0, order)
+        if self.world == 1:
+            return send, order, counts, counts
+        recv, recv_counts = exchange(send, counts, self.group)
+        return recv, order, counts, recv_counts
+
+    def _mutate(self, op: int, d_buf: int, offsets: np.ndarray) -> None:
+        words = self.engine.seq_words(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
+        recv, _, _, _ = self._route_words(words)
+        self.engine.words_op(op, recv, want_flags=False)
+
+    def insert_seqs_dev(self, d_buf: int, offsets: np.ndarray) -> None:
+        """Every rank passes ITS OWN reads; all k-mers of all ranks end up in the (global) set."""
+        self._mutate(1, d_buf, offsets)
+
+    def remove_seqs_dev(self, d_buf: int, offsets: np.ndarray) -> None:
+        self._mutate(2, d_buf, offsets)
+
+    def contains_words(self, words: torch.Tensor) -> torch.Tensor:
+        recv, order, counts, recv_counts = self._route_words(words)
+        flags = self.engine.words_op(0, recv, want_flags=True)
+        if self.world > 1:
+            back = flags.new_empty(int(counts.sum()))
+            dist.all_to_all_single(back, flags, output_split_sizes=counts.tolist(), input_split_sizes=recv_counts.tolist(), group=self.group)
+            flags = back
+        out = torch.empty_like(flags)
+        out[order] = flags  # undo the grouping: answers in the order of the local reads
+        return out
+
+    def contains_seqs_dev(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
+        """Per-k-mer answers (uint8 device tensor) for this rank's reads, in the reference's order
+        (src/cbl.rs:311-324)."""
+        words = self.engine.seq_words(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
+        return self.contains_words(words)
+
+    # host-buffer front ends (what a user of the reference calls): copy, then the device path
+    def insert_seqs(self, buf: np.ndarray, offsets: np.ndarray) -> None:
+        t = torch.from_numpy(np.ascontiguousarray(buf)).to(self.device, non_blocking=True)
+        self.insert_seqs_dev(t.data_ptr(), offsets)
+
+    def remove_seqs(self, buf: np.ndarray, offsets: np.ndarray) -> None:
+        t = torch.from_numpy(np.ascontiguousarray(buf)).to(self.device, non_blocking=True)
+        self.remove_seqs_dev(t.data_ptr(), offsets)
+
+    def contains_seqs(self, buf: np.ndarray, offsets: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        t = torch.from_numpy(np.ascontiguousarray(buf)).to(self.device, non_blocking=True)
+        ans = self.contains_seqs_dev(t.data_ptr(), offsets)
+        if out is None:
+            return ans.cpu().numpy()
+        torch.from_numpy(out)[: ans.numel()].copy_(ans)
+        return out[: ans.numel()]
+
+    # -- global scalars --------------------------------------------------------------------------
+    def local_count(self) -> int:
+        return self.engine.count()
+
+    def count(self) -> int:
+        c = torch.tensor([self.engine.count()], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(c, group=self.group)
+        return int(c.item())
+
+    def num_buckets(self) -> int:
+        nb = getattr(self.engine, "cbl", None)
+        c = torch.tensor([nb.num_buckets() if nb is not None else 0], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(c, group=self.group)
+        return int(c.item())
+
+    def stream_ptr(self) -> int:
+        return self.engine.cbl.stream_ptr()

@@ -1,0 +1,148 @@
+"""world_size-2 (and 3) gloo tests of the multi-GPU host logic in cbl_b200/sharded.py, on CPU tensors:
+prefix extraction, equal-mass splitters, routing, the all-to-all-v exchange, the answer return path
+and global count, with a stand-in engine (a Python set of words per rank fed by the CPU oracle's
+seq_words).  The GPU engine itself is covered by the -m gpu tests."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+import cbl_testutil as util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_word_prefixes_and_route():
+    sys.path.insert(0, ROOT)
+    from cbl_b200._lib import lib  # noqa: F401  (the package needs the native library to import)
+    from cbl_b200.sharded import equal_mass_splitters, route, word_prefixes
+
+    rng = np.random.default_rng(1)
+    # 64-bit words (K=29: word uses all 64 bits incl. the sign bit)
+    for k, pb in [(25, 24), (29, 24), (7, 14)]:
+        sb = 2 * k + util.pos_bits(k) - pb
+        words = [int(x) for x in rng.integers(0, 1 << 62, size=1000)] + [(1 << (2 * k + util.pos_bits(k))) - 1]
+        t = torch.tensor(np.array(words, dtype=np.uint64).view(np.int64))
+        got = word_prefixes(t, sb, pb).tolist()
+        assert got == [(w >> sb) & ((1 << pb) - 1) for w in words]
+    # 128-bit words as (lo, hi)
+    for k, pb in [(31, 24), (59, 28), (59, 24), (33, 8)]:
+        sb = 2 * k + util.pos_bits(k) - pb
+        wb = 2 * k + util.pos_bits(k)
+        words = [int.from_bytes(rng.bytes(16), "little") & ((1 << wb) - 1) for _ in range(1000)]
+        arr = np.array([[w & 0xFFFFFFFFFFFFFFFF, w >> 64] for w in words], dtype=np.uint64).view(np.int64)
+        got = word_prefixes(torch.tensor(arr), sb, pb).tolist()
+        assert got == [w >> sb for w in words]
+    pre = torch.tensor([5, 1, 9, 3, 3, 7, 0, 9])
+    sp = torch.tensor([3, 8])
+    dest, order, counts = route(pre, sp)
+    assert dest.tolist() == [1, 0, 2, 1, 1, 1, 0, 2] and counts.tolist() == [2, 4, 2]
+    assert pre[order].tolist() == [1, 0, 5, 3, 3, 7, 9, 9]  # stable grouping
+    s = equal_mass_splitters(torch.arange(1000), 4)
+    assert s.tolist() == [250, 500, 750]
+    assert equal_mass_splitters(torch.zeros(100, dtype=torch.int64), 3).tolist() == [0, 1]
+
+
+WORKER = textwrap.dedent(
+    """
+    import os, sys
+    import numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+    import cbl_testutil as util
+    from oracle.pyoracle import OracleCBL
+    from cbl_b200.sharded import ShardedCBL
+
+    K, TB, PB, CANON = {k}, {tb}, {pb}, {canon}
+
+    class SetEngine:
+        '''stand-in shard: words from the CPU oracle, membership in a Python set'''
+        device = torch.device("cpu")
+        def __init__(self):
+            self.o = OracleCBL(K, TB, PB, CANON)
+            self.words = set()
+            self.host = {{}}
+        def _to_tensor(self, lo, hi):
+            if 2 * K + util.pos_bits(K) <= 64:
+                return torch.from_numpy(lo.view(np.int64).copy())
+            return torch.from_numpy(np.stack([lo, hi], axis=1).view(np.int64).copy())
+        def _ints(self, t):
+            a = t.numpy().view(np.uint64)
+            return [int(x) for x in a] if a.ndim == 1 else [int(l) | (int(h) << 64) for l, h in a]
+        def seq_words(self, key, offsets):
+            buf = self.host[key]
+            los, his = [], []
+            for i in range(len(offsets) - 1):
+                lo, hi = self.o.seq_words(buf[int(offsets[i]):int(offsets[i + 1])])
+                los.append(lo); his.append(hi)
+            return self._to_tensor(np.concatenate(los), np.concatenate(his))
+        def words_op(self, op, words, want_flags):
+            ws = self._ints(words)
+            flags = torch.tensor([w in self.words for w in ws], dtype=torch.uint8) if want_flags else None
+            if op == 1: self.words.update(ws)
+            if op == 2: self.words.difference_update(ws)
+            return flags
+        def count(self):
+            return len(self.words)
+        def sample_words(self, n, seed):
+            self.host["sample"] = util.random_dna(n, seed)
+            return self.seq_words("sample", np.array([0, n], dtype=np.uint64))
+
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    eng = SetEngine()
+    sh = ShardedCBL(K, TB, PB, CANON, engine=eng, sample_bases=60000)
+    assert sh.splitters.numel() == world - 1
+    # every rank has its own reads; the union is the global set
+    reads = [util.random_dna(20000 + 1000 * r, seed=50 + r) for r in range(world)]
+    mine = reads[rank]
+    eng.host["mine"] = mine
+    offs = np.array([0, 7000, len(mine)], dtype=np.uint64)
+    sh.insert_seqs_dev("mine", offs)
+    ref = OracleCBL(K, TB, PB, CANON)
+    for r in range(world):
+        ref.insert_seq(reads[r][:7000]); ref.insert_seq(reads[r][7000:])
+    assert sh.count() == ref.count(), (sh.count(), ref.count())
+    # shards are disjoint, ordered by rank, and together equal the reference set
+    local = sorted(eng.words)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    flat = [w for part in gathered for w in part]
+    assert flat == sorted(flat) and flat == util.to_int_list(*ref.iter_words()), "concatenation of shards != ascending reference set"
+    sizes = [len(p) for p in gathered]
+    assert min(sizes) > 0.5 * max(sizes), f"unbalanced shards {{sizes}}"   # equal-mass splitters (SURVEY F4)
+    # contains: rank-local queries (mix of hits from OTHER ranks' reads and misses), answers in local order
+    q = np.concatenate([reads[(rank + 1) % world][3000:9000], util.random_dna(5000, seed=900 + rank)])
+    eng.host["q"] = q
+    got = sh.contains_seqs_dev("q", np.array([0, len(q)], dtype=np.uint64)).numpy()
+    exp = ref.contains_seq(q)
+    assert np.array_equal(got, exp), "sharded contains_seq != reference answers"
+    assert 0 < got.sum() < len(got)
+    # remove what rank 0 inserted, everywhere
+    eng.host["r0"] = reads[0]
+    if rank == 0:
+        sh.remove_seqs_dev("r0", np.array([0, 7000, len(reads[0])], dtype=np.uint64))
+    else:
+        eng.host["empty"] = reads[0][:K]
+        sh.remove_seqs_dev("empty", np.array([0, K], dtype=np.uint64))
+    ref.remove_seq(reads[0][:7000]); ref.remove_seq(reads[0][7000:]); 
+    assert sh.count() == ref.count()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+    """
+)
+
+
+@pytest.mark.parametrize("world,k,tb,pb,canon", [(2, 25, 64, 24, False), (2, 59, 128, 28, True), (3, 31, 128, 24, False)])
+def test_sharded_routing_gloo(tmp_path, world, k, tb, pb, canon):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, k=k, tb=tb, pb=pb, canon=canon))
+    port = 29600 + (os.getpid() + world * 7 + k) % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == world
