@@ -89,6 +89,7 @@ class Index final : public IIndex {
     uint32_t last_prefix_ = 0;  // prefix of the last bucket (for the reference's is_empty quirk)
     uint64_t bitmap_words_ = 0, n_blocks_ = 0;
     uint64_t batch_kmers_;
+    static constexpr uint64_t SUF_PAD = 16;  // suffix arrays are over-allocated: probe windows are 32-byte aligned loads
 
 public:
     explicit Index(const Config& cfg) : cfg_(cfg) {
@@ -116,7 +117,7 @@ public:
         bucket_prefix_.alloc(1, st_);
         bucket_off_.alloc(1, st_);
         bucket_off_.zero();
-        suf_.alloc(1, st_);
+        suf_.alloc(SUF_PAD, st_);
         batch_kmers_ = env_u64("CBL_BATCH_KMERS", sizeof(W) == 8 ? (1ull << 27) : (1ull << 26));
         if (batch_kmers_ > RS_MAX_KEYS) batch_kmers_ = RS_MAX_KEYS;
         if (batch_kmers_ < CHUNK_KMERS) batch_kmers_ = CHUNK_KMERS;
@@ -170,7 +171,7 @@ public:
         CUDA_CHECK(cudaMemcpyAsync(blkrank_.get(), o.blkrank_.get(), n_blocks_ * 4, cudaMemcpyDeviceToDevice, st_));
         bucket_prefix_.alloc(nb_ ? nb_ : 1, st_);
         bucket_off_.alloc((uint64_t)nb_ + 1, st_);
-        suf_.alloc(n_ ? n_ : 1, st_);
+        suf_.alloc(n_ + SUF_PAD, st_);
         if (nb_) CUDA_CHECK(cudaMemcpyAsync(bucket_prefix_.get(), o.bucket_prefix_.get(), (size_t)nb_ * 4, cudaMemcpyDeviceToDevice, st_));
         CUDA_CHECK(cudaMemcpyAsync(bucket_off_.get(), o.bucket_off_.get(), ((size_t)nb_ + 1) * 4, cudaMemcpyDeviceToDevice, st_));
         if (n_) CUDA_CHECK(cudaMemcpyAsync(suf_.get(), o.suf_.get(), n_ * sizeof(Suf), cudaMemcpyDeviceToDevice, st_));
@@ -372,7 +373,7 @@ public:
                        lb.counter.get());
         }
         // suffixes
-        ns.suf.alloc(n_new ? n_new : 1, st_);
+        ns.suf.alloc(n_new + SUF_PAD, st_);
         {
             const uint64_t V = n_ + ni;
             const uint64_t t = div_up(V, OP_TILE);
