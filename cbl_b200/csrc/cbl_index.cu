@@ -81,14 +81,15 @@ class Index final : public IIndex {
     KParams P_;
     cudaStream_t st_ = nullptr;
     cudaStream_t side_[2] = {nullptr, nullptr};
-    DevBuf<uint64_t> bitmap_;
-    DevBuf<uint32_t> blkrank_, bucket_prefix_, bucket_off_;
+    DevBuf<uint2> dir_, bucket_range_;
+    DevBuf<uint32_t> bucket_prefix_, bucket_off_;
     DevBuf<Suf> suf_;
     uint32_t nb_ = 0;
     uint64_t n_ = 0;
     uint32_t last_prefix_ = 0;  // prefix of the last bucket (for the reference's is_empty quirk)
-    uint64_t bitmap_words_ = 0, n_blocks_ = 0;
+    uint64_t n_dir_ = 0;  // directory words: 32 prefixes each
     uint64_t batch_kmers_;
+    int probe_window_ = 32;  // bytes per probe window (CBL_PROBE_WINDOW = 32 | 64)
     static constexpr uint64_t SUF_PAD = 16;  // suffix arrays are over-allocated: probe windows are 32-byte aligned loads
 
 public:
@@ -107,13 +108,11 @@ public:
         uint64_t thr = UINT64_MAX;
         CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         uint64_t bits = 1ull << cfg.prefix_bits;
-        if (bits < 256) bits = 256;
-        bitmap_words_ = bits / 64;
-        n_blocks_ = bits / 256;
-        bitmap_.alloc(bitmap_words_, st_);
-        bitmap_.zero();
-        blkrank_.alloc(n_blocks_, st_);
-        blkrank_.zero();
+        if (bits < 32) bits = 32;
+        n_dir_ = bits / 32;
+        dir_.alloc(n_dir_, st_);
+        dir_.zero();
+        bucket_range_.alloc(1, st_);
         bucket_prefix_.alloc(1, st_);
         bucket_off_.alloc(1, st_);
         bucket_off_.zero();
@@ -121,6 +120,8 @@ public:
         batch_kmers_ = env_u64("CBL_BATCH_KMERS", sizeof(W) == 8 ? (1ull << 27) : (1ull << 26));
         if (batch_kmers_ > RS_MAX_KEYS) batch_kmers_ = RS_MAX_KEYS;
         if (batch_kmers_ < CHUNK_KMERS) batch_kmers_ = CHUNK_KMERS;
+        probe_window_ = env_u64("CBL_PROBE_WINDOW", 32) == 64 ? 64 : 32;
+        if (uint64_t g = env_u64("CBL_L2_FETCH", 0)) CUDA_CHECK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
         static bool attr_done = false;
         if (!attr_done) {
             CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -131,7 +132,7 @@ public:
     }
     ~Index() override {
         cudaSetDevice(cfg_.device);
-        bitmap_.release(); blkrank_.release(); bucket_prefix_.release(); bucket_off_.release(); suf_.release();
+        dir_.release(); bucket_range_.release(); bucket_prefix_.release(); bucket_off_.release(); suf_.release();
         if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
         for (auto& s : side_) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     }
@@ -152,8 +153,8 @@ public:
 
     IndexView<Suf> view() const {
         IndexView<Suf> v;
-        v.bitmap = bitmap_.get(); v.blkrank = blkrank_.get(); v.bucket_prefix = bucket_prefix_.get();
-        v.bucket_off = bucket_off_.get(); v.suf = suf_.get(); v.nb = nb_; v.n = n_;
+        v.dir = dir_.get(); v.bucket_prefix = bucket_prefix_.get(); v.bucket_off = bucket_off_.get();
+        v.bucket_range = bucket_range_.get(); v.suf = suf_.get(); v.nb = nb_; v.n = n_;
         return v;
     }
 
@@ -167,8 +168,9 @@ public:
     }
     void copy_state_from(const Index& o) {
         nb_ = o.nb_; n_ = o.n_; last_prefix_ = o.last_prefix_;
-        CUDA_CHECK(cudaMemcpyAsync(bitmap_.get(), o.bitmap_.get(), bitmap_words_ * 8, cudaMemcpyDeviceToDevice, st_));
-        CUDA_CHECK(cudaMemcpyAsync(blkrank_.get(), o.blkrank_.get(), n_blocks_ * 4, cudaMemcpyDeviceToDevice, st_));
+        CUDA_CHECK(cudaMemcpyAsync(dir_.get(), o.dir_.get(), n_dir_ * sizeof(uint2), cudaMemcpyDeviceToDevice, st_));
+        bucket_range_.alloc(nb_ ? nb_ : 1, st_);
+        if (nb_) CUDA_CHECK(cudaMemcpyAsync(bucket_range_.get(), o.bucket_range_.get(), (size_t)nb_ * sizeof(uint2), cudaMemcpyDeviceToDevice, st_));
         bucket_prefix_.alloc(nb_ ? nb_ : 1, st_);
         bucket_off_.alloc((uint64_t)nb_ + 1, st_);
         suf_.alloc(n_ + SUF_PAD, st_);
@@ -191,13 +193,13 @@ public:
         }
     }
     // pieces of records [r0, r1) — out offsets are k-mer ranks counted from record r0
-    void build_pieces(const uint64_t* offsets, size_t r0, size_t r1, PieceList& pl) const {
+    void build_pieces(const uint64_t* offsets, size_t r0, size_t r1, PieceList& pl, uint32_t piece_kmers = PIECE_KMERS) const {
         pl = PieceList();
         pl.chunk0.push_back(0);
         for (size_t r = r0; r < r1; r++) {
             uint64_t nk = offsets[r + 1] - offsets[r] - (uint64_t)cfg_.k + 1;
-            for (uint64_t s = 0; s < nk; s += PIECE_KMERS) {
-                uint32_t m = (uint32_t)std::min<uint64_t>(PIECE_KMERS, nk - s);
+            for (uint64_t s = 0; s < nk; s += piece_kmers) {
+                uint32_t m = (uint32_t)std::min<uint64_t>(piece_kmers, nk - s);
                 pl.byte_off.push_back(offsets[r] + s);
                 pl.out_off.push_back(pl.n_kmers + s);
                 pl.kmers.push_back(m);
@@ -232,25 +234,35 @@ public:
         dp.batch.n_pieces = (uint32_t)np; dp.batch.n_chunks = ch[np];
     }
 
-    // launches the fused encode + necklace (+ probe) kernel; throws EINVAL on a non-ACGT byte
+    // launches the fused encode + necklace (+ probe) kernel (no synchronisation); *err must hold
+    // ULLONG_MAX on entry and receives the smallest offending byte offset if a non-ACGT byte is seen
+    void launch_seq_words(const SeqBatch& b, int mode, bool brute, W* d_words, uint8_t* d_flags, unsigned long long* err, cudaStream_t s) {
+        if (b.n_chunks == 0) return;
+        unsigned grid = (unsigned)std::min<uint64_t>(b.n_chunks, 1u << 30);
+        IndexView<Suf> v = view();
+        if (mode == 0) {
+            if (brute) CBL_LAUNCH((seq_words_kernel<W, Suf, 0, true, 32>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
+            else CBL_LAUNCH((seq_words_kernel<W, Suf, 0, false, 32>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
+        } else if (probe_window_ == 64) {
+            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, 64>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
+        } else {
+            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, 32>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
+        }
+    }
+    static void throw_bad_byte(unsigned long long e) {
+        throw Error(CBL_EINVAL, "non-ACGT byte in sequence near byte offset " + std::to_string(e) +
+                                    " (the GPU path rejects what the reference silently drops; see DESIGN.md)");
+    }
+    // same, synchronous: throws EINVAL on a non-ACGT byte
     void run_seq_words(const SeqBatch& b, int mode, bool brute, W* d_words, uint8_t* d_flags, cudaStream_t s) {
         if (b.n_chunks == 0) return;
         DevBuf<unsigned long long> err(1, s);
         CUDA_CHECK(cudaMemsetAsync(err.get(), 0xFF, 8, s));
-        unsigned grid = (unsigned)std::min<uint64_t>(b.n_chunks, 1u << 30);
-        IndexView<Suf> v = view();
-        if (mode == 0) {
-            if (brute) CBL_LAUNCH((seq_words_kernel<W, Suf, 0, true>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err.get());
-            else CBL_LAUNCH((seq_words_kernel<W, Suf, 0, false>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err.get());
-        } else {
-            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err.get());
-        }
+        launch_seq_words(b, mode, brute, d_words, d_flags, err.get(), s);
         unsigned long long e = 0;
         CUDA_CHECK(cudaMemcpyAsync(&e, err.get(), 8, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
-        if (e != ULLONG_MAX)
-            throw Error(CBL_EINVAL, "non-ACGT byte in sequence near byte offset " + std::to_string(e) +
-                                        " (the GPU path rejects what the reference silently drops; see DESIGN.md)");
+        if (e != ULLONG_MAX) throw_bad_byte(e);
     }
 
     // ------------------------------------------------------------------------------------------
@@ -300,8 +312,8 @@ public:
     // mutation: sorted distinct probe keys -> edits -> new directory -> new suffix array
     // ------------------------------------------------------------------------------------------
     struct NewState {
-        DevBuf<uint64_t> bitmap;
-        DevBuf<uint32_t> blkrank, bucket_prefix, bucket_off;
+        DevBuf<uint2> dir, bucket_range;
+        DevBuf<uint32_t> bucket_prefix, bucket_off;
         DevBuf<Suf> suf;
         uint32_t nb = 0;
         uint64_t n = 0;
@@ -309,10 +321,10 @@ public:
         bool changed = false;
     };
     void adopt(NewState& ns) {
-        bitmap_.swap(ns.bitmap); blkrank_.swap(ns.blkrank); bucket_prefix_.swap(ns.bucket_prefix);
+        dir_.swap(ns.dir); bucket_range_.swap(ns.bucket_range); bucket_prefix_.swap(ns.bucket_prefix);
         bucket_off_.swap(ns.bucket_off); suf_.swap(ns.suf);
         nb_ = ns.nb; n_ = ns.n; last_prefix_ = ns.last_prefix;
-        bitmap_.rebind(st_); blkrank_.rebind(st_); bucket_prefix_.rebind(st_); bucket_off_.rebind(st_); suf_.rebind(st_);
+        dir_.rebind(st_); bucket_range_.rebind(st_); bucket_prefix_.rebind(st_); bucket_off_.rebind(st_); suf_.rebind(st_);
     }
 
     // keys: sorted distinct words.  probe_ix: index they are looked up in (own view unless KEEP_ONLY).
@@ -330,13 +342,13 @@ public:
         DevBuf<uint64_t> ins_vpos(want_ins ? nk : 1, st_), del_idx(want_del ? nk : 1, st_);
         DevBuf<int> delta(nb_ ? nb_ : 1, st_);
         delta.zero();
-        ns.bitmap.alloc(bitmap_words_, st_);
-        CUDA_CHECK(cudaMemcpyAsync(ns.bitmap.get(), bitmap_.get(), bitmap_words_ * 8, cudaMemcpyDeviceToDevice, st_));
+        ns.dir.alloc(n_dir_, st_);
+        CUDA_CHECK(cudaMemcpyAsync(ns.dir.get(), dir_.get(), n_dir_ * sizeof(uint2), cudaMemcpyDeviceToDevice, st_));
         Lookback lb_ins(tiles, st_), lb_del(tiles, st_);
         DevBuf<unsigned long long> counts(4, st_);
         counts.zero();
         CBL_LAUNCH((probe_edits_kernel<W, Suf>), (unsigned)tiles, OP_THREADS, 0, st_, keys, nk, probe_ix, self, P_, mode, ins_key,
-                   ins_vpos.get(), del_idx.get(), delta.get(), (unsigned long long*)ns.bitmap.get(), lb_ins.status.get(),
+                   ins_vpos.get(), del_idx.get(), delta.get(), ns.dir.get(), lb_ins.status.get(),
                    lb_del.status.get(), lb_ins.counter.get(), counts.get());
         unsigned long long h_counts[2] = {0, 0};
         CUDA_CHECK(cudaMemcpyAsync(h_counts, counts.get(), 16, cudaMemcpyDeviceToHost, st_));
@@ -349,27 +361,27 @@ public:
 
         // directory
         if (nb_) CBL_LAUNCH(clear_emptied_kernel, (unsigned)div_up(nb_, 256), 256, 0, st_, bucket_prefix_.get(), bucket_off_.get(),
-                            delta.get(), nb_, (unsigned long long*)ns.bitmap.get());
-        ns.blkrank.alloc(n_blocks_, st_);
+                            delta.get(), nb_, ns.dir.get());
         {
-            const uint64_t t = div_up(n_blocks_, OP_TILE);
+            const uint64_t t = div_up(n_dir_, OP_TILE);
             Lookback lb(t, st_);
-            CBL_LAUNCH(rank_directory_kernel, (unsigned)t, OP_THREADS, 0, st_, ns.bitmap.get(), n_blocks_, ns.blkrank.get(),
-                       lb.status.get(), lb.counter.get(), counts.get() + 2);
+            CBL_LAUNCH(rank_directory_kernel, (unsigned)t, OP_THREADS, 0, st_, ns.dir.get(), n_dir_, lb.status.get(), lb.counter.get(),
+                       counts.get() + 2);
         }
         const uint64_t nb_new = read_u64(counts.get() + 2);
         DevBuf<uint32_t> size_new(nb_new + 1, st_);
         size_new.zero();
         ns.bucket_prefix.alloc(nb_new ? nb_new : 1, st_);
         if (nb_) CBL_LAUNCH(fill_sizes_old_kernel, (unsigned)div_up(nb_, 256), 256, 0, st_, bucket_prefix_.get(), bucket_off_.get(),
-                            delta.get(), nb_, ns.bitmap.get(), ns.blkrank.get(), size_new.get(), ns.bucket_prefix.get());
-        if (ni) CBL_LAUNCH((fill_sizes_ins_kernel<W>), (unsigned)div_up(ni, 256), 256, 0, st_, ins_key, ni, P_, bitmap_.get(),
-                           ns.bitmap.get(), ns.blkrank.get(), size_new.get(), ns.bucket_prefix.get());
+                            delta.get(), nb_, ns.dir.get(), size_new.get(), ns.bucket_prefix.get());
+        if (ni) CBL_LAUNCH((fill_sizes_ins_kernel<W>), (unsigned)div_up(ni, 256), 256, 0, st_, ins_key, ni, P_, dir_.get(), ns.dir.get(),
+                           size_new.get(), ns.bucket_prefix.get());
         ns.bucket_off.alloc(nb_new + 1, st_);
+        ns.bucket_range.alloc(nb_new ? nb_new : 1, st_);
         {
             const uint64_t t = div_up(nb_new + 1, OP_TILE);
             Lookback lb(t, st_);
-            CBL_LAUNCH(scan_sizes_kernel, (unsigned)t, OP_THREADS, 0, st_, size_new.get(), nb_new, ns.bucket_off.get(), lb.status.get(),
+            CBL_LAUNCH(scan_sizes_kernel, (unsigned)t, OP_THREADS, 0, st_, size_new.get(), nb_new, ns.bucket_off.get(), ns.bucket_range.get(), lb.status.get(),
                        lb.counter.get());
         }
         // suffixes
@@ -477,37 +489,124 @@ public:
             mutate_seqs_dev(d.get(), nbytes, off.data(), q - r, remove ? EDIT_DEL : EDIT_INS);
         });
     }
+    // Host buffers -> answers on the host, software-pipelined over N_SLOTS streams: while one group's
+    // kernel runs, the next group's reads are on their way in and the previous group's answers on
+    // their way out (H2D and D2H use separate copy engines).  Nothing blocks the host until the end;
+    // with pinned host memory the copies are true DMA, with pageable memory the driver stages them.
+    static constexpr int N_SLOTS = 3;
+    struct Slot {
+        cudaStream_t s = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf<uint8_t> seq, flags;
+        DevBuf<uint64_t> byte_off, out_off, chunk0;
+        DevBuf<uint32_t> kmers;
+        DevBuf<unsigned long long> err;
+        uint64_t *h_byte = nullptr, *h_out = nullptr, *h_chunk0 = nullptr;  // pinned staging for the piece arrays
+        uint32_t* h_kmers = nullptr;
+        size_t cap_pieces = 0;
+        bool used = false;
+        void free_host() {
+            if (h_byte) cudaFreeHost(h_byte);
+            if (h_out) cudaFreeHost(h_out);
+            if (h_chunk0) cudaFreeHost(h_chunk0);
+            if (h_kmers) cudaFreeHost(h_kmers);
+            h_byte = h_out = h_chunk0 = nullptr;
+            h_kmers = nullptr;
+        }
+    };
     void contains_seqs(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint8_t* out) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         check_records(offsets, n_seqs);
-        CUDA_CHECK(cudaStreamSynchronize(st_));  // index state is final before the side streams read it
-        // two side streams alternate so the copies of group g+1 overlap the kernel of group g
-        int slot = 0;
-        uint64_t kmer_base = 0;
-        std::string first_error;
-        int32_t first_code = 0;
-        for_each_group(offsets, n_seqs, [&](size_t r, size_t q) {
-            cudaStream_t s = side_[slot];
-            slot ^= 1;
-            const uint64_t b0 = offsets[r], nbytes = offsets[q] - b0;
-            std::vector<uint64_t> off(q - r + 1);
-            for (size_t i = r; i <= q; i++) off[i - r] = offsets[i] - b0;
-            PieceList pl;
-            build_pieces(off.data(), 0, q - r, pl);
-            DevBuf<uint8_t> d(nbytes + 64, s), flags(pl.n_kmers, s);
-            CUDA_CHECK(cudaMemcpyAsync(d.get(), seq + b0, nbytes, cudaMemcpyHostToDevice, s));
-            DevPieces dp;
-            upload_pieces(pl, 0, pl.kmers.size(), 0, d.get(), nbytes, dp, s);
-            try {
-                run_seq_words(dp.batch, 1, false, nullptr, flags.get(), s);
-            } catch (const Error& e) {
-                if (first_error.empty()) { first_error = e.what(); first_code = e.code; }
+        CUDA_CHECK(cudaStreamSynchronize(st_));  // index state is final before the pipeline streams read it
+        // cut all records into pieces of <= piece_kmers k-mers, then group consecutive pieces
+        const uint64_t group_kmers = std::max<uint64_t>(CHUNK_KMERS, env_u64("CBL_GROUP_BYTES", 32ull << 20));
+        const uint32_t piece_kmers = (uint32_t)std::min<uint64_t>(PIECE_KMERS, std::max<uint64_t>(CHUNK_KMERS, (group_kmers / 4) / CHUNK_KMERS * CHUNK_KMERS));
+        PieceList pl;
+        build_pieces(offsets, 0, n_seqs, pl, piece_kmers);
+        const size_t np = pl.kmers.size();
+        if (np == 0) return;
+        // groups [g0, g1) of pieces
+        std::vector<std::pair<size_t, size_t>> groups;
+        size_t max_pieces = 0;
+        uint64_t max_bytes = 0, max_kmers = 0;
+        for (size_t p = 0; p < np;) {
+            size_t q = p;
+            uint64_t nk = 0;
+            while (q < np && (q == p || nk + pl.kmers[q] <= group_kmers)) { nk += pl.kmers[q]; q++; }
+            groups.push_back({p, q});
+            max_pieces = std::max(max_pieces, q - p);
+            max_kmers = std::max(max_kmers, nk);
+            max_bytes = std::max<uint64_t>(max_bytes, pl.byte_off[q - 1] + pl.kmers[q - 1] + cfg_.k - 1 - pl.byte_off[p]);
+            p = q;
+        }
+        Slot slots[N_SLOTS];
+        struct Cleanup {
+            Slot* sl;
+            ~Cleanup() {
+                for (int i = 0; i < N_SLOTS; i++) {
+                    if (sl[i].s) cudaStreamSynchronize(sl[i].s);
+                    sl[i].seq.release(); sl[i].flags.release(); sl[i].byte_off.release(); sl[i].out_off.release();
+                    sl[i].chunk0.release(); sl[i].kmers.release(); sl[i].err.release();
+                    if (sl[i].s) cudaStreamSynchronize(sl[i].s);
+                    sl[i].free_host();
+                    if (sl[i].done) cudaEventDestroy(sl[i].done);
+                    if (sl[i].s) cudaStreamDestroy(sl[i].s);
+                }
             }
-            CUDA_CHECK(cudaMemcpyAsync(out + kmer_base, flags.get(), pl.n_kmers, cudaMemcpyDeviceToHost, s));
-            kmer_base += pl.n_kmers;
-        });
-        for (auto& s : side_) CUDA_CHECK(cudaStreamSynchronize(s));
-        if (!first_error.empty()) throw Error(first_code, first_error);
+        } cleanup{slots};
+        const int n_slots = (int)std::min<size_t>(N_SLOTS, groups.size());
+        for (int i = 0; i < n_slots; i++) {
+            Slot& sl = slots[i];
+            CUDA_CHECK(cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+            sl.seq.alloc(max_bytes + 64, sl.s);
+            sl.flags.alloc(max_kmers, sl.s);
+            sl.byte_off.alloc(max_pieces, sl.s); sl.out_off.alloc(max_pieces, sl.s); sl.chunk0.alloc(max_pieces + 1, sl.s);
+            sl.kmers.alloc(max_pieces, sl.s);
+            sl.err.alloc(1, sl.s);
+            CUDA_CHECK(cudaMemsetAsync(sl.err.get(), 0xFF, 8, sl.s));
+            CUDA_CHECK(cudaMallocHost((void**)&sl.h_byte, max_pieces * 8));
+            CUDA_CHECK(cudaMallocHost((void**)&sl.h_out, max_pieces * 8));
+            CUDA_CHECK(cudaMallocHost((void**)&sl.h_chunk0, (max_pieces + 1) * 8));
+            CUDA_CHECK(cudaMallocHost((void**)&sl.h_kmers, max_pieces * 4));
+        }
+        for (size_t g = 0; g < groups.size(); g++) {
+            Slot& sl = slots[g % n_slots];
+            if (sl.used) CUDA_CHECK(cudaEventSynchronize(sl.done));  // staging buffers of this slot are free again
+            const size_t p0 = groups[g].first, p1 = groups[g].second, m = p1 - p0;
+            const uint64_t b0 = pl.byte_off[p0];
+            const uint64_t nbytes = pl.byte_off[p1 - 1] + pl.kmers[p1 - 1] + cfg_.k - 1 - b0;
+            const uint64_t k0 = pl.out_off[p0];
+            uint64_t nk = 0;
+            for (size_t i = 0; i < m; i++) {
+                sl.h_byte[i] = pl.byte_off[p0 + i] - b0;
+                sl.h_out[i] = pl.out_off[p0 + i] - k0;
+                sl.h_kmers[i] = pl.kmers[p0 + i];
+                sl.h_chunk0[i] = pl.chunk0[p0 + i] - pl.chunk0[p0];
+                nk += pl.kmers[p0 + i];
+            }
+            sl.h_chunk0[m] = pl.chunk0[p1] - pl.chunk0[p0];
+            CUDA_CHECK(cudaMemcpyAsync(sl.seq.get(), seq + b0, nbytes, cudaMemcpyHostToDevice, sl.s));
+            CUDA_CHECK(cudaMemcpyAsync(sl.byte_off.get(), sl.h_byte, m * 8, cudaMemcpyHostToDevice, sl.s));
+            CUDA_CHECK(cudaMemcpyAsync(sl.out_off.get(), sl.h_out, m * 8, cudaMemcpyHostToDevice, sl.s));
+            CUDA_CHECK(cudaMemcpyAsync(sl.chunk0.get(), sl.h_chunk0, (m + 1) * 8, cudaMemcpyHostToDevice, sl.s));
+            CUDA_CHECK(cudaMemcpyAsync(sl.kmers.get(), sl.h_kmers, m * 4, cudaMemcpyHostToDevice, sl.s));
+            SeqBatch b;
+            b.seq = sl.seq.get(); b.seq_end = sl.seq.get() + nbytes;
+            b.piece_byte = sl.byte_off.get(); b.piece_out = sl.out_off.get(); b.piece_kmers = sl.kmers.get(); b.piece_chunk0 = sl.chunk0.get();
+            b.n_pieces = (uint32_t)m; b.n_chunks = sl.h_chunk0[m];
+            launch_seq_words(b, 1, false, nullptr, sl.flags.get(), sl.err.get(), sl.s);
+            CUDA_CHECK(cudaMemcpyAsync(out + k0, sl.flags.get(), nk, cudaMemcpyDeviceToHost, sl.s));
+            CUDA_CHECK(cudaEventRecord(sl.done, sl.s));
+            sl.used = true;
+        }
+        unsigned long long errs[N_SLOTS];
+        for (int i = 0; i < n_slots; i++) {
+            errs[i] = ULLONG_MAX;
+            CUDA_CHECK(cudaMemcpyAsync(&errs[i], slots[i].err.get(), 8, cudaMemcpyDeviceToHost, slots[i].s));
+        }
+        for (int i = 0; i < n_slots; i++) CUDA_CHECK(cudaStreamSynchronize(slots[i].s));
+        for (int i = 0; i < n_slots; i++) if (errs[i] != ULLONG_MAX) throw_bad_byte(errs[i]);
     }
     void seq_words(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint64_t* lo, uint64_t* hi, bool brute) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
@@ -661,8 +760,7 @@ public:
         return res.release();
     }
     void clear() {
-        bitmap_.zero();
-        blkrank_.zero();
+        dir_.zero();
         bucket_off_.alloc(1, st_);
         bucket_off_.zero();
         nb_ = 0; n_ = 0; last_prefix_ = 0;

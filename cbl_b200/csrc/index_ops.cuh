@@ -1,4 +1,4 @@
-// Kernels k3b-k8: unique, edit generation (probe), bucket directory rebuild (bitmap + popcount rank
+// Kernels k3b-k8: unique, edit generation (probe), bucket directory rebuild (bitvector + popcount rank
 // directory + CSR offsets), the streaming merge / anti-merge that rewrites the suffix array, and the
 // CSR -> words expansion used by iter/export and the set operations.
 //
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(OP_THREADS) unique_kernel(const W* __restrict_
 //                 absent there                                         (&=)
 // Outputs: ins_key / ins_vpos (virtual position = insertion point + number of earlier inserts),
 // del_idx (ascending target positions), per-target-bucket size deltas, and the bits of brand-new
-// prefixes OR-ed into new_bitmap (a copy of the target's bitmap).
+// prefixes OR-ed into new_dir (a copy of the target's directory; ranks are recomputed afterwards).
 // ---------------------------------------------------------------------------------------------
 enum : int { EDIT_INS = 1, EDIT_DEL = 2, EDIT_KEEP_ONLY = 4 };
 
@@ -68,7 +68,7 @@ template <class W, class Suf>
 __global__ void __launch_bounds__(OP_THREADS) probe_edits_kernel(
     const W* __restrict__ keys, uint64_t n, IndexView<Suf> ix, IndexView<Suf> target, KParams P, int mode,
     W* __restrict__ ins_key, uint64_t* __restrict__ ins_vpos, uint64_t* __restrict__ del_idx, int* __restrict__ delta,
-    unsigned long long* __restrict__ new_bitmap, volatile uint64_t* status_ins, volatile uint64_t* status_del,
+    uint2* __restrict__ new_dir, volatile uint64_t* status_ins, volatile uint64_t* status_del,
     uint32_t* tile_counter, unsigned long long* __restrict__ counts /* [0]=n_ins [1]=n_del */) {
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_excl;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(OP_THREADS) probe_edits_kernel(
                     del[i] = true;
                     apos[i] = idx;
                     uint32_t prefix = (uint32_t)(k[i] >> P.suffix_bits), trank;
-                    bitmap_test_rank(target.bitmap, target.blkrank, prefix, trank);
+                    dir_test_rank(target.dir, prefix, trank);
                     atomicAdd(delta + trank, -1);
                 }
             } else {
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(OP_THREADS) probe_edits_kernel(
                     if (r.prefix_present) atomicAdd(delta + r.rank, 1);
                     else {
                         uint32_t prefix = (uint32_t)(k[i] >> P.suffix_bits);
-                        atomicOr(new_bitmap + (prefix >> 6), 1ull << (prefix & 63));
+                        atomicOr(dir_bits_word(new_dir, prefix), 1u << (prefix & 31));
                     }
                 }
                 if (r.found && (mode & EDIT_DEL)) {
@@ -136,20 +136,19 @@ __global__ void __launch_bounds__(OP_THREADS) probe_edits_kernel(
 // ---------------------------------------------------------------------------------------------
 // (a) clear the bits of buckets that end up empty
 __global__ void clear_emptied_kernel(const uint32_t* __restrict__ bucket_prefix, const uint32_t* __restrict__ bucket_off,
-                                     const int* __restrict__ delta, uint32_t nb, unsigned long long* __restrict__ new_bitmap) {
+                                     const int* __restrict__ delta, uint32_t nb, uint2* __restrict__ new_dir) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
     int sz = (int)(bucket_off[r + 1] - bucket_off[r]) + delta[r];
     if (sz == 0) {
         uint32_t p = bucket_prefix[r];
-        atomicAnd(new_bitmap + (p >> 6), ~(1ull << (p & 63)));
+        atomicAnd(dir_bits_word(new_dir, p), ~(1u << (p & 31)));
     }
 }
 
-// (b) rank directory: blkrank[b] = number of set bits before 256-bit block b; *nb_out = total set bits.
+// (b) rank directory: dir[i].y = number of set bits before word i; *nb_out = total set bits.
 // Single pass: per-thread popcounts, warp-shuffle scan, block scan, decoupled look-back across tiles.
-__global__ void __launch_bounds__(OP_THREADS) rank_directory_kernel(const uint64_t* __restrict__ bitmap, uint64_t n_blocks,
-                                                                    uint32_t* __restrict__ blkrank, volatile uint64_t* status,
+__global__ void __launch_bounds__(OP_THREADS) rank_directory_kernel(uint2* __restrict__ dir, uint64_t n_words, volatile uint64_t* status,
                                                                     uint32_t* tile_counter, unsigned long long* __restrict__ nb_out) {
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_excl;
@@ -159,13 +158,8 @@ __global__ void __launch_bounds__(OP_THREADS) rank_directory_kernel(const uint64
     uint32_t c[OP_ITEMS], cnt = 0;
 #pragma unroll
     for (int i = 0; i < OP_ITEMS; i++) {
-        const uint64_t blk = base + i;
-        c[i] = 0;
-        if (blk < n_blocks) {
-            const ulonglong2* w = reinterpret_cast<const ulonglong2*>(bitmap + (blk << 2));
-            ulonglong2 a = __ldg(w), b = __ldg(w + 1);
-            c[i] = __popcll(a.x) + __popcll(a.y) + __popcll(b.x) + __popcll(b.y);
-        }
+        const uint64_t w = base + i;
+        c[i] = w < n_words ? __popc(dir[w].x) : 0;
         cnt += c[i];
     }
     uint32_t total;
@@ -174,24 +168,23 @@ __global__ void __launch_bounds__(OP_THREADS) rank_directory_kernel(const uint64
     uint32_t run = (uint32_t)excl + off;
 #pragma unroll
     for (int i = 0; i < OP_ITEMS; i++) {
-        const uint64_t blk = base + i;
-        if (blk < n_blocks) blkrank[blk] = run;
+        const uint64_t w = base + i;
+        if (w < n_words) dir[w].y = run;
         run += c[i];
     }
-    if (threadIdx.x == 0 && (uint64_t)(tile + 1) * OP_TILE >= n_blocks && (uint64_t)tile * OP_TILE < n_blocks) *nb_out = excl + total;
+    if (threadIdx.x == 0 && (uint64_t)(tile + 1) * OP_TILE >= n_words && (uint64_t)tile * OP_TILE < n_words) *nb_out = excl + total;
 }
 
 // (c) surviving old buckets -> their new rank
 __global__ void fill_sizes_old_kernel(const uint32_t* __restrict__ bucket_prefix, const uint32_t* __restrict__ bucket_off,
-                                      const int* __restrict__ delta, uint32_t nb, const uint64_t* __restrict__ new_bitmap,
-                                      const uint32_t* __restrict__ new_blkrank, uint32_t* __restrict__ size_new,
-                                      uint32_t* __restrict__ prefix_new) {
+                                      const int* __restrict__ delta, uint32_t nb, const uint2* __restrict__ new_dir,
+                                      uint32_t* __restrict__ size_new, uint32_t* __restrict__ prefix_new) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
     int sz = (int)(bucket_off[r + 1] - bucket_off[r]) + delta[r];
     if (sz > 0) {
         uint32_t p = bucket_prefix[r], nr;
-        bitmap_test_rank(new_bitmap, new_blkrank, p, nr);
+        dir_test_rank(new_dir, p, nr);
         size_new[nr] = (uint32_t)sz;
         prefix_new[nr] = p;
     }
@@ -199,16 +192,16 @@ __global__ void fill_sizes_old_kernel(const uint32_t* __restrict__ bucket_prefix
 
 // (d) inserted keys whose prefix did not exist before -> count them into their new bucket
 template <class W>
-__global__ void fill_sizes_ins_kernel(const W* __restrict__ ins_key, uint64_t ni, KParams P, const uint64_t* __restrict__ old_bitmap,
-                                      const uint64_t* __restrict__ new_bitmap, const uint32_t* __restrict__ new_blkrank,
-                                      uint32_t* __restrict__ size_new, uint32_t* __restrict__ prefix_new) {
+__global__ void fill_sizes_ins_kernel(const W* __restrict__ ins_key, uint64_t ni, KParams P, const uint2* __restrict__ old_dir,
+                                      const uint2* __restrict__ new_dir, uint32_t* __restrict__ size_new,
+                                      uint32_t* __restrict__ prefix_new) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ni) return;
     uint32_t p = (uint32_t)(ins_key[i] >> P.suffix_bits);
-    bool was = old_bitmap ? ((__ldg(old_bitmap + (p >> 6)) >> (p & 63)) & 1) : false;
+    const bool was = (__ldg(old_dir + (p >> 5)).x >> (p & 31)) & 1u;
     if (!was) {
         uint32_t nr;
-        bitmap_test_rank(new_bitmap, new_blkrank, p, nr);
+        dir_test_rank(new_dir, p, nr);
         atomicAdd(size_new + nr, 1u);
         prefix_new[nr] = p;
     }
@@ -216,7 +209,8 @@ __global__ void fill_sizes_ins_kernel(const W* __restrict__ ins_key, uint64_t ni
 
 // (e) exclusive scan of u32 sizes -> u32 offsets (n entries in, n+1 out: out[n] = total)
 __global__ void __launch_bounds__(OP_THREADS) scan_sizes_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ out,
-                                                                volatile uint64_t* status, uint32_t* tile_counter) {
+                                                                uint2* __restrict__ range, volatile uint64_t* status,
+                                                                uint32_t* tile_counter) {
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_excl;
     __shared__ uint32_t s_tmp[33];
@@ -235,6 +229,7 @@ __global__ void __launch_bounds__(OP_THREADS) scan_sizes_kernel(const uint32_t* 
 #pragma unroll
     for (int i = 0; i < OP_ITEMS; i++) {
         if (base + i <= n) out[base + i] = run;  // includes the terminal entry out[n]
+        if (base + i < n) range[base + i] = make_uint2(run, run + c[i]);
         run += c[i];
     }
 }

@@ -79,7 +79,7 @@ template <> __device__ __forceinline__ u128 cut_window<u128>(uint64_t A, uint64_
 
 // MODE 0: write words (W) to out_words.   MODE 1: probe the index, write one byte per k-mer.
 // BRUTE: use the normative brute-force necklace instead of the fast one (debug / cross-check).
-template <class W, class Suf, int MODE, bool BRUTE>
+template <class W, class Suf, int MODE, bool BRUTE, int WB>
 __global__ void __launch_bounds__(SW_THREADS) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
                                                                uint8_t* __restrict__ out_flags, IndexView<Suf> ix,
                                                                unsigned long long* __restrict__ err_pos) {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(SW_THREADS) seq_words_kernel(SeqBatch b, KPara
             if (active) {
                 W word = kmer_to_word<W>(x, P, BRUTE);
                 if (MODE == 0) ow[slot] = word;
-                else of[slot] = probe_key<W, Suf>(ix, P, word).found ? 1 : 0;
+                else of[slot] = probe_key<W, Suf, WB>(ix, P, word).found ? 1 : 0;
             }
         }
         __syncthreads();  // s_piece / s_fwd reuse in the next grid-stride iteration
