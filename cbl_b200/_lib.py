@@ -56,6 +56,8 @@ SIGNATURES = {
     "cbl_seq_words_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t, vp]),
     "cbl_words_op_dev": (C.c_int32, [vp, C.c_int32, vp, C.c_size_t, vp]),
     "cbl_export_words_dev": (C.c_int32, [vp, C.c_uint64, C.c_uint64, vp]),
+    "cbl_route_words_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, vp, vp, u64p]),
+    "cbl_gather_u8_dev": (C.c_int32, [vp, vp, vp, C.c_size_t, vp]),
     "cbl_word_bytes": (C.c_int32, [vp, i32p]),
     "cbl_suffix_bits": (C.c_int32, [vp, i32p]),
     "cbl_seq_words": (C.c_int32, [vp, vp, u64p, C.c_size_t, u64p, u64p, C.c_int32]),

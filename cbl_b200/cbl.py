@@ -196,6 +196,16 @@ class CBL:
     def words_op_dev(self, op: int, d_words: int, n: int, d_out: int = 0) -> None:
         self._chk(self._L.cbl_words_op_dev(self._h, op, d_words, n, d_out))
 
+    def route_words_dev(self, d_words: int, n: int, splitters: np.ndarray, d_send: int, d_pos: int = 0) -> np.ndarray:
+        """Stable partition of n device words by owner rank; returns the per-destination counts."""
+        sp = np.ascontiguousarray(splitters, dtype=np.uint32)
+        counts = np.zeros(len(sp) + 1, dtype=np.uint64)
+        self._chk(self._L.cbl_route_words_dev(self._h, d_words, n, sp.ctypes.data_as(u32p), len(sp), d_send, d_pos, counts.ctypes.data_as(u64p)))
+        return counts
+
+    def gather_u8_dev(self, d_src: int, d_pos: int, n: int, d_out: int) -> None:
+        self._chk(self._L.cbl_gather_u8_dev(self._h, d_src, d_pos, n, d_out))
+
     def export_words_dev(self, start: int, count: int, d_out: int) -> None:
         self._chk(self._L.cbl_export_words_dev(self._h, start, count, d_out))
 

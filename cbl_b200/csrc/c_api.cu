@@ -384,6 +384,22 @@ int32_t cbl_words_op_dev(cbl_t* h, int32_t op, const void* d_words, size_t n, ui
 int32_t cbl_export_words_dev(cbl_t* h, uint64_t start, uint64_t count, void* d_out) {
     return guard(h, [&] { need(h, "handle"); if (count) need(d_out, "d_out"); h->ix->export_words_dev(start, count, 0, d_out); h->ix->sync(); });
 }
+int32_t cbl_route_words_dev(cbl_t* h, const void* d_words, size_t n, const uint32_t* splitters, uint32_t n_splitters, void* d_send,
+                            uint32_t* d_pos, uint64_t* counts) {
+    return guard(h, [&] {
+        need(h, "handle"); need(counts, "counts");
+        if (n_splitters) need(splitters, "splitters");
+        if (n) { need(d_words, "d_words"); need(d_send, "d_send"); }
+        h->ix->route_words_dev(d_words, n, splitters, n_splitters, d_send, d_pos, counts);
+    });
+}
+int32_t cbl_gather_u8_dev(cbl_t* h, const uint8_t* d_src, const uint32_t* d_pos, size_t n, uint8_t* d_out) {
+    return guard(h, [&] {
+        need(h, "handle");
+        if (n) { need(d_src, "d_src"); need(d_pos, "d_pos"); need(d_out, "d_out"); }
+        h->ix->gather_u8_dev(d_src, d_pos, n, d_out);
+    });
+}
 int32_t cbl_word_bytes(const cbl_t* h, int32_t* out) {
     return guard(mut(h), [&] {
         need(h, "handle"); need(out, "out");

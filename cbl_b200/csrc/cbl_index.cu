@@ -124,8 +124,8 @@ public:
         if (uint64_t g = env_u64("CBL_L2_FETCH", 0)) CUDA_CHECK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
         static bool attr_done = false;
         if (!attr_done) {
-            CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute(radix_pass_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, ByteDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr_done = true;
         }
         CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -286,8 +286,8 @@ public:
         for (int p = 0; p < n_pass; p++) {
             status.zero();
             counter.zero();
-            CBL_LAUNCH((radix_pass_kernel<W, false>), (unsigned)tiles, RS_THREADS, smem, st_, src, dst, nullptr, nullptr, n, 8 * p,
-                       hist.get() + (size_t)p * 256, status.get(), counter.get());
+            CBL_LAUNCH((radix_pass_kernel<W, false, ByteDigit<W>>), (unsigned)tiles, RS_THREADS, smem, st_, src, dst, nullptr, nullptr, n,
+                       ByteDigit<W>{8 * p}, hist.get() + (size_t)p * 256, status.get(), counter.get(), (uint32_t*)nullptr);
             std::swap(src, dst);
         }
         return src;
@@ -672,6 +672,43 @@ public:
         CUDA_CHECK(cudaMemcpyAsync(d.get(), h.data(), n * sizeof(W), cudaMemcpyHostToDevice, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
         words_op_dev(1, d.get(), n, nullptr);
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // multi-GPU routing building blocks: stable partition of words by owner rank + answer gather
+    // ------------------------------------------------------------------------------------------
+    void route_words_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* d_send, uint32_t* d_pos,
+                         uint64_t* counts) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        if (n_split > ROUTE_MAX_SPLIT) throw Error(CBL_EINVAL, "too many splitters");
+        for (uint32_t i = 0; i <= n_split; i++) counts[i] = 0;
+        if (n == 0) return;
+        if (n > RS_MAX_KEYS) throw Error(CBL_EINVAL, "route batch too large (max 2^30 - 1 words per call)");
+        DestDigit<W> dg;
+        dg.suffix_bits = P_.suffix_bits;
+        dg.n_split = n_split;
+        for (int i = 0; i < ROUTE_MAX_SPLIT; i++) dg.split[i] = i < (int)n_split ? splitters[i] : 0xFFFFFFFFu;
+        DevBuf<unsigned long long> hist(256, st_);
+        hist.zero();
+        unsigned hgrid = (unsigned)std::min<uint64_t>(div_up(n, 256 * 8), 148 * 16);
+        CBL_LAUNCH((route_hist_kernel<W>), hgrid, 256, 0, st_, (const W*)d_words, n, dg, hist.get());
+        unsigned long long h[ROUTE_MAX_SPLIT + 1];
+        CUDA_CHECK(cudaMemcpyAsync(h, hist.get(), sizeof(h), cudaMemcpyDeviceToHost, st_));
+        CBL_LAUNCH(radix_scan_hist_kernel, 1, 256, 0, st_, hist.get());
+        const uint64_t tiles = div_up(n, RsTile<W>::TILE);
+        DevBuf<uint32_t> status(tiles * 256, st_), counter(1, st_);
+        status.zero();
+        counter.zero();
+        CBL_LAUNCH((radix_pass_kernel<W, false, DestDigit<W>>), (unsigned)tiles, RS_THREADS, sizeof(W) * RsTile<W>::TILE, st_, (const W*)d_words,
+                   (W*)d_send, nullptr, nullptr, n, dg, hist.get(), status.get(), counter.get(), d_pos);
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        for (uint32_t i = 0; i <= n_split; i++) counts[i] = h[i];
+    }
+    void gather_u8_dev(const uint8_t* d_src, const uint32_t* d_pos, uint64_t n, uint8_t* d_out) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        if (n == 0) return;
+        CBL_LAUNCH(gather_u8_kernel, (unsigned)div_up(n, 256), 256, 0, st_, d_src, d_pos, n, d_out);
         CUDA_CHECK(cudaStreamSynchronize(st_));
     }
 

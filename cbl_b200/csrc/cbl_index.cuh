@@ -46,6 +46,10 @@ public:
     virtual void kmers_op(int op /*0 contains,1 insert,2 remove*/, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out) = 0;
     // words (already transformed) — used by the sharded multi-GPU path after the all-to-all
     virtual void words_op_dev(int op, const void* d_words, uint64_t n, uint8_t* d_out) = 0;
+    // multi-GPU routing: stable partition of words by owner rank (dest = #splitters <= prefix)
+    virtual void route_words_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* d_send,
+                                 uint32_t* d_pos, uint64_t* counts) = 0;
+    virtual void gather_u8_dev(const uint8_t* d_src, const uint32_t* d_pos, uint64_t n, uint8_t* d_out) = 0;
     // set operations
     virtual IIndex* setop(int op, IIndex* other) = 0;
     virtual void setop_assign(int op, IIndex* other) = 0;

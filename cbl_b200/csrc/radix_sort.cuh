@@ -19,6 +19,26 @@ template <class W> struct RsTile { static constexpr int ITEMS = sizeof(W) == 8 ?
 
 template <class W> __device__ __forceinline__ uint32_t digit_of(W key, int shift) { return (uint32_t)(key >> shift) & 255u; }
 
+// digit functors for the scatter pass: a byte of the key (LSD sort) or the owner rank of the word's
+// prefix (multi-GPU routing: dest = number of splitters <= prefix, i.e. contiguous prefix ranges)
+template <class W> struct ByteDigit {
+    int shift;
+    __device__ __forceinline__ uint32_t operator()(W key) const { return (uint32_t)(key >> shift) & 255u; }
+};
+constexpr int ROUTE_MAX_SPLIT = 15;
+template <class W> struct DestDigit {
+    int suffix_bits;
+    uint32_t n_split;
+    uint32_t split[ROUTE_MAX_SPLIT];
+    __device__ __forceinline__ uint32_t operator()(W key) const {
+        const uint32_t prefix = (uint32_t)(key >> suffix_bits);
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < ROUTE_MAX_SPLIT; i++) d += (i < (int)n_split) && (split[i] <= prefix);
+        return d;
+    }
+};
+
 // All digit histograms in one read of the keys.  hist[pass][256] (u64, zeroed by the caller).
 template <class W>
 __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const W* __restrict__ keys, uint64_t n, int n_pass,
@@ -52,11 +72,14 @@ __global__ void __launch_bounds__(256) radix_scan_hist_kernel(unsigned long long
 }
 
 // One scatter pass.  status[tile][256] must be zero on entry; tile_counter zero.
-template <class W, bool HAS_VAL>
+// HAS_VAL: a u32 payload travels with every key.  pos_out (may be null): receives, for every input
+// slot, the slot its key was moved to (used by the multi-GPU router to bring answers back).
+template <class W, bool HAS_VAL, class DigitFn>
 __global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(const W* __restrict__ in, W* __restrict__ out,
                                                                 const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
-                                                                uint64_t n, int shift, const unsigned long long* __restrict__ digit_base,
-                                                                volatile uint32_t* status, uint32_t* tile_counter) {
+                                                                uint64_t n, DigitFn digit, const unsigned long long* __restrict__ digit_base,
+                                                                volatile uint32_t* status, uint32_t* tile_counter,
+                                                                uint32_t* __restrict__ pos_out) {
     constexpr int ITEMS = RsTile<W>::ITEMS;
     constexpr int TILE = RsTile<W>::TILE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -86,7 +109,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(const W* __restr
         const bool valid = local < tile_n;
         key[i] = valid ? in[tile_base + local] : (W)0;
         if (HAS_VAL) val[i] = valid ? vin[tile_base + local] : 0u;
-        const uint32_t d = digit_of<W>(key[i], shift);
+        const uint32_t d = digit(key[i]);
         const unsigned peers = __match_any_sync(0xffffffffu, d | (valid ? 0u : 0x100u));
         const uint32_t lt = __popc(peers & lanemask_lt());
         uint32_t base = valid ? s_whist[warp][d] : 0u;
@@ -131,10 +154,11 @@ __global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(const W* __restr
     for (int i = 0; i < ITEMS; i++) {
         const int local = warp * (32 * ITEMS) + i * 32 + lane;
         if (local < tile_n) {
-            const uint32_t d = digit_of<W>(key[i], shift);
+            const uint32_t d = digit(key[i]);
             const uint32_t pos = s_dstart[d] + s_whist[warp][d] + rnk[i];
             s_keys[pos] = key[i];
             if (HAS_VAL) s_vals[pos] = val[i];
+            if (pos_out) pos_out[tile_base + local] = (uint32_t)(s_goff[d] + (long long)pos);
         }
     }
     __syncthreads();
@@ -145,12 +169,37 @@ __global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(const W* __restr
         const int idx = i * RS_THREADS + threadIdx.x;
         if (idx < tile_n) {
             const W k = s_keys[idx];
-            const uint32_t d = digit_of<W>(k, shift);
+            const uint32_t d = digit(k);
             const long long g = s_goff[d] + idx;
             out[g] = k;
             if (HAS_VAL) vout[g] = s_vals[idx];
         }
     }
+}
+
+// per-destination counts for the router (<= 16 destinations): registers -> warp reduce -> atomics
+template <class W>
+__global__ void __launch_bounds__(256) route_hist_kernel(const W* __restrict__ keys, uint64_t n, DestDigit<W> digit,
+                                                         unsigned long long* __restrict__ hist /*[256], zeroed*/) {
+    uint32_t cnt[ROUTE_MAX_SPLIT + 1];
+#pragma unroll
+    for (int i = 0; i <= ROUTE_MAX_SPLIT; i++) cnt[i] = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t d = digit(keys[i]);
+#pragma unroll
+        for (int j = 0; j <= ROUTE_MAX_SPLIT; j++) cnt[j] += (d == (uint32_t)j);
+    }
+#pragma unroll
+    for (int j = 0; j <= ROUTE_MAX_SPLIT; j++) {
+        uint32_t c = warp_sum(cnt[j]);
+        if (lane_id() == 0 && c) atomicAdd(&hist[j], (unsigned long long)c);
+    }
+}
+
+__global__ void gather_u8_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ pos, uint64_t n, uint8_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[pos[i]];
 }
 
 }  // namespace cbl

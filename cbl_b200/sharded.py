@@ -118,6 +118,22 @@ class GpuEngine:
     def count(self) -> int:
         return self.cbl.count()
 
+    # hand-written router kernels (stable partition by owner rank + answer gather) instead of the
+    # generic torch bucketize / argsort / index_select path
+    def route(self, words: torch.Tensor, splitters: np.ndarray):
+        n = words.shape[0]
+        send = torch.empty_like(words)
+        pos = torch.empty(n, dtype=torch.int32, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        counts = self.cbl.route_words_dev(words.data_ptr(), n, splitters, send.data_ptr(), pos.data_ptr())
+        return send, pos, counts
+
+    def gather(self, src: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(pos.shape[0], dtype=torch.uint8, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.cbl.gather_u8_dev(src.data_ptr(), pos.data_ptr(), pos.shape[0], out.data_ptr())
+        return out
+
     def sample_words(self, n_bases: int, seed: int) -> torch.Tensor:
         g = torch.Generator(device=self.device)
         g.manual_seed(seed)
@@ -154,13 +170,21 @@ class ShardedCBL:
 
     # -- routing ---------------------------------------------------------------------------------
     def _route_words(self, words: torch.Tensor):
-        pre = word_prefixes(words, self.suffix_bits, self.prefix_bits)
-        _, order, counts = route(pre, self.splitters)
-        send = words.index_select(0, order)
+        """-> (words received by this rank, pos: slot of every local word in the send buffer,
+        send counts, recv counts)."""
+        if hasattr(self.engine, "route"):
+            send, pos, counts_np = self.engine.route(words, self.splitters.cpu().numpy().astype(np.uint32))
+            counts = torch.from_numpy(counts_np.astype(np.int64)).to(self.device)
+        else:  # generic torch path (CPU tests / stand-in engines)
+            pre = word_prefixes(words, self.suffix_bits, self.prefix_bits)
+            _, order, counts = route(pre, self.splitters)
+            send = words.index_select(0, order)
+            pos = torch.empty_like(order)
+            pos[order] = torch.arange(order.numel(), device=order.device)
         if self.world == 1:
-            return send, order, counts, counts
+            return send, pos, counts, counts
         recv, recv_counts = exchange(send, counts, self.group)
-        return recv, order, counts, recv_counts
+        return recv, pos, counts, recv_counts
 
     def _mutate(self, op: int, d_buf: int, offsets: np.ndarray) -> None:
         words = self.engine.seq_words(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
@@ -175,15 +199,16 @@ class ShardedCBL:
         self._mutate(2, d_buf, offsets)
 
     def contains_words(self, words: torch.Tensor) -> torch.Tensor:
-        recv, order, counts, recv_counts = self._route_words(words)
+        recv, pos, counts, recv_counts = self._route_words(words)
         flags = self.engine.words_op(0, recv, want_flags=True)
         if self.world > 1:
             back = flags.new_empty(int(counts.sum()))
             dist.all_to_all_single(back, flags, output_split_sizes=counts.tolist(), input_split_sizes=recv_counts.tolist(), group=self.group)
             flags = back
-        out = torch.empty_like(flags)
-        out[order] = flags  # undo the grouping: answers in the order of the local reads
-        return out
+        # answers in the order of the local reads: out[i] = flags[pos[i]]
+        if hasattr(self.engine, "gather"):
+            return self.engine.gather(flags, pos)
+        return flags[pos.long()]
 
     def contains_seqs_dev(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
         """Per-k-mer answers (uint8 device tensor) for this rank's reads, in the reference's order

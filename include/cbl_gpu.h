@@ -107,6 +107,13 @@ int32_t cbl_seq_words_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offset
 /* op: 0 contains (d_out required), 1 insert, 2 remove (d_out optional = membership before the call) */
 int32_t cbl_words_op_dev(cbl_t* h, int32_t op, const void* d_words, size_t n, uint8_t* d_out);
 int32_t cbl_export_words_dev(cbl_t* h, uint64_t start, uint64_t count, void* d_out);
+/* router: stable partition of n words by owner rank, dest = number of splitters <= prefix (contiguous
+ * prefix ranges).  d_send: the words grouped by destination; d_pos (may be NULL): for every input word
+ * the slot it went to; counts (host, n_splitters+1): words per destination.  n < 2^30 per call. */
+int32_t cbl_route_words_dev(cbl_t* h, const void* d_words, size_t n, const uint32_t* splitters, uint32_t n_splitters, void* d_send,
+                            uint32_t* d_pos, uint64_t* counts);
+/* d_out[i] = d_src[d_pos[i]] — puts the answers that came back from the owners into read order */
+int32_t cbl_gather_u8_dev(cbl_t* h, const uint8_t* d_src, const uint32_t* d_pos, size_t n, uint8_t* d_out);
 int32_t cbl_word_bytes(const cbl_t* h, int32_t* out);      /* 8 or 16: size of one device word */
 int32_t cbl_suffix_bits(const cbl_t* h, int32_t* out);
 

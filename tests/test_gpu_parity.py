@@ -346,3 +346,29 @@ def test_large_roundtrip_properties(gpu, k, tb, pb, n):
     assert g.count() == cnt
     g.remove_seq(seq)
     assert g.is_empty() and g.count() == 0 and not g.contains_seq(seq[:100000]).any()
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU building blocks on one GPU: router (stable partition by owner rank) + answer gather
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,tb,pb", [(25, 64, 24), (59, 128, 28)])
+def test_route_and_gather(gpu, k, tb, pb):
+    import torch
+
+    from cbl_b200.sharded import GpuEngine, equal_mass_splitters, route, word_prefixes
+
+    eng = GpuEngine(k, tb, pb, False, 0)
+    sb = 2 * k + util.pos_bits(k) - pb
+    words = eng.sample_words(300_000, seed=5)
+    pre = word_prefixes(words, sb, pb)
+    for world in (1, 2, 8):
+        sp = equal_mass_splitters(pre, world)
+        send, pos, counts = eng.route(words, sp.cpu().numpy().astype(np.uint32))
+        _, order, tcounts = route(pre, sp)
+        assert counts.tolist() == tcounts.tolist()
+        assert torch.equal(send, words.index_select(0, order)), "router must be a STABLE partition by owner"
+        assert torch.equal(send[pos.long()], words), "pos maps every word to its slot"
+        flags = (torch.arange(send.shape[0], device=send.device) % 251).to(torch.uint8)
+        assert torch.equal(eng.gather(flags, pos), flags[pos.long()])
+        if world > 1:
+            assert counts.min() > 0.8 * counts.max()  # equal-mass splitters balance random DNA
