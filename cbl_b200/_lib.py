@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcbl_gpu.so")
+# CBL_GPU_LIB: developer override to load an experimental build of the same library (still CUDA-only)
+LIB_PATH = os.environ.get("CBL_GPU_LIB") or os.path.join(_HERE, "csrc", "libcbl_gpu.so")
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)

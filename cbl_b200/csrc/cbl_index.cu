@@ -84,12 +84,13 @@ class Index final : public IIndex {
     DevBuf<uint2> dir_, bucket_range_;
     DevBuf<uint32_t> bucket_prefix_, bucket_off_;
     DevBuf<Suf> suf_;
+    DevBuf<int8_t> sub_;      // interpolation corrections for the membership probe, rebuilt lazily
+    bool sub_valid_ = false;
     uint32_t nb_ = 0;
     uint64_t n_ = 0;
     uint32_t last_prefix_ = 0;  // prefix of the last bucket (for the reference's is_empty quirk)
     uint64_t n_dir_ = 0;  // directory words: 32 prefixes each
     uint64_t batch_kmers_;
-    int probe_window_ = 32;  // bytes per probe window (CBL_PROBE_WINDOW = 32 | 64)
     static constexpr uint64_t SUF_PAD = 16;  // suffix arrays are over-allocated: probe windows are 32-byte aligned loads
 
 public:
@@ -117,10 +118,12 @@ public:
         bucket_off_.alloc(1, st_);
         bucket_off_.zero();
         suf_.alloc(SUF_PAD, st_);
+        suf_.zero();
+        sub_.alloc(4, st_);
+        sub_.zero();
         batch_kmers_ = env_u64("CBL_BATCH_KMERS", sizeof(W) == 8 ? (1ull << 27) : (1ull << 26));
         if (batch_kmers_ > RS_MAX_KEYS) batch_kmers_ = RS_MAX_KEYS;
         if (batch_kmers_ < CHUNK_KMERS) batch_kmers_ = CHUNK_KMERS;
-        probe_window_ = env_u64("CBL_PROBE_WINDOW", 32) == 64 ? 64 : 32;
         if (uint64_t g = env_u64("CBL_L2_FETCH", 0)) CUDA_CHECK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
         static bool attr_done = false;
         if (!attr_done) {
@@ -132,7 +135,7 @@ public:
     }
     ~Index() override {
         cudaSetDevice(cfg_.device);
-        dir_.release(); bucket_range_.release(); bucket_prefix_.release(); bucket_off_.release(); suf_.release();
+        dir_.release(); bucket_range_.release(); bucket_prefix_.release(); bucket_off_.release(); suf_.release(); sub_.release();
         if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
         for (auto& s : side_) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     }
@@ -154,8 +157,16 @@ public:
     IndexView<Suf> view() const {
         IndexView<Suf> v;
         v.dir = dir_.get(); v.bucket_prefix = bucket_prefix_.get(); v.bucket_off = bucket_off_.get();
-        v.bucket_range = bucket_range_.get(); v.suf = suf_.get(); v.nb = nb_; v.n = n_;
+        v.bucket_range = bucket_range_.get(); v.suf = suf_.get(); v.sub = sub_.get(); v.nb = nb_; v.n = n_;
         return v;
+    }
+    // (re)build the probe's correction bytes if the set changed since they were last computed
+    void ensure_sub() {
+        if (sub_valid_) return;
+        const uint64_t n_slots = (n_ >> SUB_SHIFT) + 4;
+        sub_.alloc(n_slots, st_);
+        CBL_LAUNCH((build_sub_kernel<Suf>), (unsigned)div_up(n_slots, 256), 256, 0, st_, view(), P_.suffix_bits, sub_.get(), n_slots);
+        sub_valid_ = true;
     }
 
     IIndex* clone() override {
@@ -168,6 +179,7 @@ public:
     }
     void copy_state_from(const Index& o) {
         nb_ = o.nb_; n_ = o.n_; last_prefix_ = o.last_prefix_;
+        sub_valid_ = false;
         CUDA_CHECK(cudaMemcpyAsync(dir_.get(), o.dir_.get(), n_dir_ * sizeof(uint2), cudaMemcpyDeviceToDevice, st_));
         bucket_range_.alloc(nb_ ? nb_ : 1, st_);
         if (nb_) CUDA_CHECK(cudaMemcpyAsync(bucket_range_.get(), o.bucket_range_.get(), (size_t)nb_ * sizeof(uint2), cudaMemcpyDeviceToDevice, st_));
@@ -241,12 +253,10 @@ public:
         unsigned grid = (unsigned)std::min<uint64_t>(b.n_chunks, 1u << 30);
         IndexView<Suf> v = view();
         if (mode == 0) {
-            if (brute) CBL_LAUNCH((seq_words_kernel<W, Suf, 0, true, 32>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
-            else CBL_LAUNCH((seq_words_kernel<W, Suf, 0, false, 32>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
-        } else if (probe_window_ == 64) {
-            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, 64>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
+            if (brute) CBL_LAUNCH((seq_words_kernel<W, Suf, 0, true, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
+            else CBL_LAUNCH((seq_words_kernel<W, Suf, 0, false, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
         } else {
-            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, 32>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
+            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
         }
     }
     static void throw_bad_byte(unsigned long long e) {
@@ -324,6 +334,7 @@ public:
         dir_.swap(ns.dir); bucket_range_.swap(ns.bucket_range); bucket_prefix_.swap(ns.bucket_prefix);
         bucket_off_.swap(ns.bucket_off); suf_.swap(ns.suf);
         nb_ = ns.nb; n_ = ns.n; last_prefix_ = ns.last_prefix;
+        sub_valid_ = false;
         dir_.rebind(st_); bucket_range_.rebind(st_); bucket_prefix_.rebind(st_); bucket_off_.rebind(st_); suf_.rebind(st_);
     }
 
@@ -451,6 +462,7 @@ public:
         PieceList pl;
         build_pieces(offsets, 0, n_seqs, pl);
         if (pl.kmers.empty()) return;
+        ensure_sub();
         DevPieces dp;
         upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, st_);
         run_seq_words(dp.batch, 1, false, nullptr, d_out, st_);
@@ -517,6 +529,7 @@ public:
     void contains_seqs(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint8_t* out) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         check_records(offsets, n_seqs);
+        ensure_sub();
         CUDA_CHECK(cudaStreamSynchronize(st_));  // index state is final before the pipeline streams read it
         // cut all records into pieces of <= piece_kmers k-mers, then group consecutive pieces
         const uint64_t group_kmers = std::max<uint64_t>(CHUNK_KMERS, env_u64("CBL_GROUP_BYTES", 32ull << 20));
@@ -639,6 +652,7 @@ public:
     void words_op_dev(int op, const void* d_words, uint64_t n, uint8_t* d_out) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         if (n == 0) return;
+        if (d_out) ensure_sub();
         if (d_out) CBL_LAUNCH((probe_words_kernel<W, Suf>), (unsigned)div_up(n, 256), 256, 0, st_, (const W*)d_words, n, view(), P_, d_out);
         if (op == 0) return;
         uint64_t done = 0;
@@ -797,6 +811,7 @@ public:
         return res.release();
     }
     void clear() {
+        sub_valid_ = false;
         dir_.zero();
         bucket_off_.alloc(1, st_);
         bucket_off_.zero();
@@ -829,12 +844,14 @@ IIndex* make_index(const Config& cfg) {
     CUDA_CHECK(cudaGetDeviceCount(&ndev));
     if (cfg.device < 0 || cfg.device >= ndev) throw Error(CBL_EINVAL, "no such CUDA device");
     // device key = smallest of u64 / u128 that holds the word, independent of the host-side T
-    if (word <= 64) {
-        if (sb <= 32) return new Index<uint64_t, uint32_t>(cfg);
-        return new Index<uint64_t, uint64_t>(cfg);
-    }
+    if (word <= 64 && sb <= 32) return new Index<uint64_t, uint32_t>(cfg);
+#ifdef CBL_FAST_BUILD  // developer builds only (make FAST=1): one instantiation, quick to compile
+    throw Error(CBL_EINVAL, "this is a FAST developer build: only u64 words with <= 32-bit suffixes are compiled in");
+#else
+    if (word <= 64) return new Index<uint64_t, uint64_t>(cfg);
     if (sb <= 64) return new Index<u128, uint64_t>(cfg);
     return new Index<u128, u128>(cfg);
+#endif
 }
 
 }  // namespace cbl

@@ -354,7 +354,37 @@ __global__ void __launch_bounds__(OP_THREADS) expand_kernel(IndexView<Suf> ix, K
 template <class W, class Suf>
 __global__ void probe_words_kernel(const W* __restrict__ words, uint64_t n, IndexView<Suf> ix, KParams P, uint8_t* __restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = probe_key<W, Suf>(ix, P, words[i]).found ? 1 : 0;
+    if (i < n) out[i] = contains_key<W, Suf>(ix, P, words[i]) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Interpolation corrections for the membership probe (index_view.cuh): one signed byte per group of
+// SUB_GROUP suffixes.  Slot q belongs to the bucket that holds element q * SUB_GROUP; if it is one of
+// the bucket's first 2^eb slots it stores  lower_bound(boundary j * 2^(32-eb)) - straight-line prediction.
+// ---------------------------------------------------------------------------------------------
+template <class Suf>
+__global__ void __launch_bounds__(256) build_sub_kernel(IndexView<Suf> ix, int suffix_bits, int8_t* __restrict__ sub, uint64_t n_slots) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_slots) return;
+    int dv = 0;
+    const uint64_t pos = q << SUB_SHIFT;
+    if (pos < ix.n && ix.nb) {
+        const uint32_t r = (uint32_t)(upper_bound_dev<uint32_t>(ix.bucket_off, (uint64_t)ix.nb + 1, (uint32_t)pos) - 1);
+        const uint32_t start = ix.bucket_off[r], end = ix.bucket_off[r + 1];
+        const SubSlots ss = sub_slots(start, end);
+        const uint32_t j = (uint32_t)q - ss.first;
+        if (ss.eb > 0 && j > 0 && j < (1u << ss.eb)) {
+            const uint32_t kb = j << (32 - ss.eb);
+            uint32_t lo = start, hi = end;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (key32<Suf>(ix.suf[mid], suffix_bits) < kb) lo = mid + 1; else hi = mid;
+            }
+            dv = (int)(lo - start) - (int)__umulhi(kb, end - start);
+            dv = min(max(dv, -127), 127);
+        }
+    }
+    sub[q] = (int8_t)dv;
 }
 
 // bucket sizes (prefix, size) — a by-product of the CSR offsets (src/wordset/mod.rs:258-263)

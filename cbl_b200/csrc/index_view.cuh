@@ -11,10 +11,58 @@
 //   bucket_range[nb]        uint2 {start, end} of bucket r — the same information laid out so a probe
 //                                 gets both bounds with one 8-byte load
 //   suf[n]                  Suf   suffixes, ascending inside every bucket => ascending word order overall
+//   sub[n / 16 + 2]         i8    read-only accelerator for contains: per group of 16 suffixes the deviation
+//                                 of the bucket's empirical CDF from a straight line (built lazily)
 #pragma once
 #include "scan.cuh"
 
 namespace cbl {
+
+// ---- L2 residency hints ----------------------------------------------------------------------------
+// The probe's lookup tables (directory, bucket ranges, correction bytes: tens of MB) are re-read all
+// the time and should stay in the 126 MB L2, while suffix windows are touched once per lookup and
+// would otherwise wash the tables out.  CBL_L2_POLICY=1: tables evict_last, windows evict_first.
+#ifndef CBL_L2_POLICY
+#define CBL_L2_POLICY 1
+#endif
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint2 ldg_keep(const uint2* p) {
+#if CBL_L2_POLICY
+    uint2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(l2_policy_keep()));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ int ldg_keep(const int8_t* p) {
+#if CBL_L2_POLICY
+    int v;
+    asm("ld.global.nc.L2::cache_hint.s8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_keep()));
+    return v;
+#else
+    return (int)__ldg(p);
+#endif
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+#if CBL_L2_POLICY
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(l2_policy_stream()));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 
 template <class Suf>
 struct IndexView {
@@ -23,6 +71,7 @@ struct IndexView {
     const uint32_t* bucket_off;
     const uint2* bucket_range;
     const Suf* suf;
+    const int8_t* sub;   // interpolation corrections, one per SUB_GROUP suffixes (see "membership probe" below)
     uint32_t nb;
     uint64_t n;
 };
@@ -76,7 +125,7 @@ template <class Suf, int WB> __device__ __forceinline__ void load_window(const S
     constexpr int EPC = 16 / (int)sizeof(Suf);
     uint4 x[WB / 16];
 #pragma unroll
-    for (int c = 0; c < WB / 16; c++) x[c] = __ldg(q + c);
+    for (int c = 0; c < WB / 16; c++) x[c] = ldg_stream(q + c);
 #pragma unroll
     for (int c = 0; c < WB / 16; c++) unpack16<Suf>(x[c], &e[c * EPC]);
 }
@@ -154,6 +203,132 @@ __device__ __forceinline__ ProbeResult probe_key(const IndexView<Suf>& ix, const
     bucket_search<Suf, WB>(ix.suf, range.x, range.y, s, P.suffix_bits, r.found, pos);
     r.pos = pos;
     return r;
+}
+
+// ---- membership probe (contains_seq / contains) --------------------------------------------------
+// Only "is it there" is needed, so the search is specialised: the slot of suffix s inside its bucket
+// [start, end) is predicted as  start + floor(key32(s) * span / 2^32) + corr  where corr comes from
+// `sub`: the bucket owns the slots  first = ceil(start/16) .. end/16  of the sub array; the first
+// 2^eb of them (eb = floor(log2(#slots))) hold, for the suffix-space boundaries j * 2^(32-eb), the
+// signed difference between the true lower-bound position of that boundary and the straight-line
+// prediction (clamped to i8).  Interpolating between two neighbouring corrections leaves an error of
+// a couple of slots (binomial noise inside one ~16-element group), so the first aligned 32-byte
+// window resolves ~4 of 5 lookups and one neighbouring window nearly all the rest.  Everything is
+// exact: a wrong prediction only costs extra windows, and after PROBE_MAX_IT windows the search
+// falls back to plain bisection of what is left.
+#ifndef CBL_SUB_SHIFT
+#define CBL_SUB_SHIFT 4
+#endif
+constexpr int SUB_SHIFT = CBL_SUB_SHIFT;
+constexpr int SUB_GROUP = 1 << SUB_SHIFT;
+
+struct SubSlots {
+    uint32_t first;  // index of the bucket's first slot in sub[]
+    int eb;          // log2 of the number of boundaries kept (0 => no correction for this bucket)
+};
+__device__ __forceinline__ SubSlots sub_slots(uint32_t start, uint32_t end) {
+    SubSlots r;
+    r.first = (start + SUB_GROUP - 1) >> SUB_SHIFT;
+    const int slots = (int)(end >> SUB_SHIFT) - (int)r.first;
+    r.eb = slots >= 2 ? 31 - __clz(slots) : 0;
+    return r;
+}
+
+// predicted slot (relative to start) of the suffix with monotone 32-bit image k32 inside bucket
+// [start, end).  Branch-free (the two byte loads are always in bounds: sub[] has n/16 + 4 entries) so the
+// caller can keep several lookups in flight.
+__device__ __forceinline__ uint32_t predict_slot(const int8_t* __restrict__ sub, uint32_t start, uint32_t end, uint32_t k32) {
+    const uint32_t span = end - start;
+    const SubSlots ss = sub_slots(start, end);
+    const uint64_t t = (uint64_t)k32 << ss.eb;
+    const uint32_t j = (uint32_t)(t >> 32);
+    const int frac = (int)((uint32_t)t >> 24);
+    const int d0 = ldg_keep(sub + ss.first + j);
+    int d1 = ldg_keep(sub + ss.first + j + 1);
+    d1 = (j + 1 < (1u << ss.eb)) ? d1 : 0;
+    const int corr = ss.eb > 0 ? d0 + (((d1 - d0) * frac + 128) >> 8) : 0;
+    const int guess = (int)__umulhi(k32, span) + corr;
+    return (uint32_t)min(max(guess, 0), max((int)span - 1, 0));
+}
+
+// window evaluation.  Returns 1 found, 0 proven absent, -1 undecided (L/R/g updated for the next window).
+template <class Suf, int WB>
+__device__ __forceinline__ int eval_window(const Suf (&e)[Window<Suf, WB>::N], uint32_t base, Suf s, uint32_t k32, int suffix_bits,
+                                           uint32_t span, uint32_t& L, uint32_t& R, uint32_t& g) {
+    constexpr int WN = Window<Suf, WB>::N;
+    if (base >= L && base + WN <= R) {  // window entirely inside the open range (the common case); e[] ascending
+        if (s < e[0]) {
+            R = base;
+            if (R <= L) return 0;
+            const uint32_t d = __umulhi(key32<Suf>(e[0], suffix_bits) - k32, span);
+            g = base - 1 - min(d, base - 1 - L);
+            return -1;
+        }
+        if (s > e[WN - 1]) {
+            L = base + WN;
+            if (R <= L) return 0;
+            const uint32_t d = __umulhi(k32 - key32<Suf>(e[WN - 1], suffix_bits), span);
+            g = L + min(d, R - 1 - L);
+            return -1;
+        }
+        bool eq = false;
+#pragma unroll
+        for (int i = 0; i < WN; i++) eq |= e[i] == s;
+        return eq ? 1 : 0;
+    }
+    const uint32_t v0 = max(L, base), v1 = min(R, base + WN);  // valid slots of the window
+    uint32_t n_lt = 0;
+    bool eq = false;
+#pragma unroll
+    for (int i = 0; i < WN; i++) {
+        const uint32_t idx = base + i;
+        const bool ok = idx >= v0 && idx < v1;
+        n_lt += ok && e[i] < s;
+        eq |= ok && e[i] == s;
+    }
+    if (eq) return 1;
+    if (n_lt == 0) { R = v0; if (R <= L) return 0; g = R - 1; return -1; }
+    if (n_lt == v1 - v0) { L = v1; if (R <= L) return 0; g = L; return -1; }
+    return 0;
+}
+
+// continue a lookup whose first window did not decide it
+template <class Suf, int WB>
+__device__ __noinline__ bool contains_slow(const Suf* __restrict__ suf, uint32_t L, uint32_t R, uint32_t g, Suf s, uint32_t k32,
+                                           int suffix_bits, uint32_t span, uint32_t end) {
+    constexpr int WN = Window<Suf, WB>::N;
+    for (int it = 0; it < PROBE_MAX_IT; it++) {
+        const uint32_t base = g & ~(uint32_t)(WN - 1);
+        Suf e[WN];
+        load_window<Suf, WB>(suf + base, e);
+        const int r = eval_window<Suf, WB>(e, base, s, k32, suffix_bits, span, L, R, g);
+        if (r >= 0) return r != 0;
+    }
+    while (L < R) {  // exact fallback
+        const uint32_t mid = L + ((R - L) >> 1);
+        if (suf[mid] < s) L = mid + 1; else R = mid;
+    }
+    return L < end && suf[L] == s;
+}
+
+// one complete lookup (word-level entry points; the sequence kernel stages the same steps by hand)
+template <class W, class Suf, int WB = 32>
+__device__ __forceinline__ bool contains_key(const IndexView<Suf>& ix, const KParams& P, W key) {
+    constexpr int WN = Window<Suf, WB>::N;
+    uint32_t prefix, rank;
+    Suf s;
+    split_key<W, Suf>(key, P, prefix, s);
+    if (ix.nb == 0 || !dir_test_rank(ix.dir, prefix, rank)) return false;
+    const uint2 range = ldg_keep(ix.bucket_range + rank);
+    const uint32_t k32 = key32<Suf>(s, P.suffix_bits), span = range.y - range.x;
+    uint32_t g = range.x + predict_slot(ix.sub, range.x, range.y, k32);
+    uint32_t L = range.x, R = range.y;
+    const uint32_t base = g & ~(uint32_t)(WN - 1);
+    Suf e[WN];
+    load_window<Suf, WB>(ix.suf + base, e);
+    const int r = eval_window<Suf, WB>(e, base, s, k32, P.suffix_bits, span, L, R, g);
+    if (r >= 0) return r != 0;
+    return contains_slow<Suf, WB>(ix.suf, L, R, g, s, k32, P.suffix_bits, span, range.y);
 }
 
 }  // namespace cbl

@@ -16,6 +16,11 @@ namespace cbl {
 
 constexpr int CHUNK_KMERS = 2048;  // src/cbl.rs:67 CHUNK_SIZE
 constexpr int SW_THREADS = 64;
+constexpr int PENDING_CAP = 64;   // per-warp queue of undecided lookups (power of two, >= 63)
+template <class Suf> struct alignas(sizeof(Suf) == 4 ? 8 : 16) PendingKey {
+    Suf s;
+    uint32_t slot_it;
+};
 
 struct SeqBatch {
     const uint8_t* seq;          // concatenated record bytes (device)
@@ -79,13 +84,78 @@ template <> __device__ __forceinline__ u128 cut_window<u128>(uint64_t A, uint64_
 
 // MODE 0: write words (W) to out_words.   MODE 1: probe the index, write one byte per k-mer.
 // BRUTE: use the normative brute-force necklace instead of the fast one (debug / cross-check).
-template <class W, class Suf, int MODE, bool BRUTE, int WB>
-__global__ void __launch_bounds__(SW_THREADS) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
+// U: k-mers per lane processed together.  In MODE 1 the U lookups advance in lock step (directory
+// words, bucket ranges, correction bytes, suffix windows), each stage issuing U independent loads.
+// Measured on B200: U = 1 with high occupancy (40 registers) beats U = 2 / 4 (80 / 120 registers);
+// only U = 1 is instantiated.
+#ifndef CBL_SW_MIN_BLOCKS
+#define CBL_SW_MIN_BLOCKS 24   // fused probe: latency bound, occupancy beats a few spilled registers (measured)
+#endif
+template <class W, class Suf, int MODE, bool BRUTE, int WB, int U>
+__global__ void __launch_bounds__(SW_THREADS, (MODE == 1 && U == 1) ? CBL_SW_MIN_BLOCKS : 1) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
                                                                uint8_t* __restrict__ out_flags, IndexView<Suf> ix,
                                                                unsigned long long* __restrict__ err_pos) {
+    static_assert(32 % U == 0, "U must divide 32");
+    constexpr int WN = Window<Suf, WB>::N;
+    constexpr int QN = MODE == 1 ? PENDING_CAP : 1;
     __shared__ uint32_t s_fwd[2][32];
     __shared__ uint32_t s_piece;
+    // MODE 1: answers of the chunk (written out coalesced at the end) and, per warp, the queue of
+    // lookups their first window did not decide.  Those are not finished on the spot (that would
+    // stall the other lanes of the warp, 4 of 5 of which are already done) but collected and worked
+    // off 32 at a time, one window per lane per round.
+    __shared__ uint8_t s_flags[MODE == 1 ? CHUNK_KMERS : 4];
+    __shared__ uint4 q_a[2][QN];                 // {L, R, g, span}
+    __shared__ PendingKey<Suf> q_b[2][QN];       // {suffix, slot | rounds << 16}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t q_head = 0, q_count = 0;  // warp-uniform
+
+    // enqueue the lanes with `und` set (warp-collective)
+    auto q_push = [&](bool und, Suf s, uint32_t L, uint32_t R, uint32_t g, uint32_t span, uint32_t slot_it) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, und);
+        if (und) {
+            const uint32_t i = (q_head + q_count + __popc(bal & lanemask_lt())) & (QN - 1);
+            q_a[warp][i] = make_uint4(L, R, g, span);
+            PendingKey<Suf> pk;
+            pk.s = s;
+            pk.slot_it = slot_it;
+            q_b[warp][i] = pk;
+        }
+        q_count += __popc(bal);
+        __syncwarp();
+    };
+    // one round: the first min(count, 32) queued lookups each examine one more window (warp-collective)
+    auto q_drain = [&]() {
+        const uint32_t take = min(q_count, 32u);
+        const bool mine = (uint32_t)lane < take;
+        const uint32_t i = (q_head + lane) & (QN - 1);
+        const uint4 a = q_a[warp][i];
+        const PendingKey<Suf> pk = q_b[warp][i];
+        __syncwarp();
+        q_head = (q_head + take) & (QN - 1);
+        q_count -= take;
+        const Suf s = pk.s;
+        uint32_t L = a.x, R = a.y, g = a.z, slot_it = pk.slot_it;
+        bool und = false;
+        if (mine) {
+            const uint32_t base = g & ~(uint32_t)(WN - 1);
+            Suf e[WN];
+            load_window<Suf, WB>(ix.suf + base, e);
+            int r = eval_window<Suf, WB>(e, base, s, key32<Suf>(s, P.suffix_bits), P.suffix_bits, a.w, L, R, g);
+            slot_it += 1u << 16;
+            if (r < 0 && (slot_it >> 16) >= (uint32_t)PROBE_MAX_IT) {  // exact fallback: bisect what is left
+                const uint32_t R0 = R;  // everything at or beyond R0 is known to be > s
+                while (L < R) {
+                    const uint32_t mid = L + ((R - L) >> 1);
+                    if (ix.suf[mid] < s) L = mid + 1; else R = mid;
+                }
+                r = (L < R0 && ix.suf[L] == s) ? 1 : 0;
+            }
+            if (r >= 0) s_flags[slot_it & 0xFFFFu] = (uint8_t)r;
+            else und = true;
+        }
+        q_push(und, s, L, R, g, a.w, slot_it);
+    };
     for (uint64_t chunk = blockIdx.x; chunk < b.n_chunks; chunk += gridDim.x) {
         if (threadIdx.x == 0) s_piece = (uint32_t)(upper_bound_dev<uint64_t>(b.piece_chunk0, (uint64_t)b.n_pieces + 1, chunk) - 1);
         __syncthreads();
@@ -110,14 +180,18 @@ __global__ void __launch_bounds__(SW_THREADS) seq_words_kernel(SeqBatch b, KPara
         }
         if (bad) atomicMin(err_pos, (unsigned long long)(b.piece_byte[piece] + ks + off));
 
+        // Wd1 / Wd2: the packed words one and two lanes further on (wrapping into the halo words held
+        // by lanes 0 and 1), so the window loops need plain broadcasts only
+        const uint64_t Wd1 = __shfl_sync(0xffffffffu, lane == 0 ? H : Wd, (lane + 1) & 31);
+        const uint64_t Wd2 = __shfl_sync(0xffffffffu, lane < 2 ? H : Wd, (lane + 2) & 31);
         const int kbase = 1024 * warp;
         uint32_t fwd_before = 0, nfwd_total = 0;
         if (P.canonical) {
             // pass 1: parity of every window -> ballots, so output slots are known up front
             for (int j = 0; j < 32; j++) {
                 uint64_t A = __shfl_sync(0xffffffffu, Wd, j);
-                uint64_t B = __shfl_sync(0xffffffffu, (j + 1 < 32) ? Wd : H, (j + 1) & 31);
-                uint64_t C = __shfl_sync(0xffffffffu, (j + 2 < 32) ? Wd : H, (j + 2) & 31);
+                uint64_t B = __shfl_sync(0xffffffffu, Wd1, j);
+                uint64_t C = __shfl_sync(0xffffffffu, Wd2, j);
                 W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
                 bool active = kbase + 32 * j + lane < m;
                 uint32_t bal = __ballot_sync(0xffffffffu, active && !(popc_w(x) & 1));
@@ -130,27 +204,81 @@ __global__ void __launch_bounds__(SW_THREADS) seq_words_kernel(SeqBatch b, KPara
             nfwd_total = c0 + c1;
             fwd_before = warp == 0 ? 0 : c0;
         }
-        for (int j = 0; j < 32; j++) {
-            if (kbase + 32 * j >= m) break;  // warp-uniform
-            uint64_t A = __shfl_sync(0xffffffffu, Wd, j);
-            uint64_t B = __shfl_sync(0xffffffffu, (j + 1 < 32) ? Wd : H, (j + 1) & 31);
-            uint64_t C = __shfl_sync(0xffffffffu, (j + 2 < 32) ? Wd : H, (j + 2) & 31);
-            const int kidx = kbase + 32 * j + lane;
-            const bool active = kidx < m;
-            W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
-            uint32_t slot = (uint32_t)kidx;
-            if (P.canonical) {
-                const uint32_t bal = s_fwd[warp][j];
-                const uint32_t fb = fwd_before + __popc(bal & lanemask_lt());
-                const bool is_fwd = (bal >> lane) & 1;
-                slot = is_fwd ? fb : nfwd_total + ((uint32_t)kidx - fb);
-                fwd_before += __popc(bal);
+        for (int j0 = 0; j0 < 32; j0 += U) {
+            if (kbase + 32 * j0 >= m) break;  // warp-uniform
+            W word[U];
+            uint32_t slot[U];
+            bool active[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int j = j0 + u;
+                uint64_t A = __shfl_sync(0xffffffffu, Wd, j);
+                uint64_t B = __shfl_sync(0xffffffffu, Wd1, j);
+                uint64_t C = __shfl_sync(0xffffffffu, Wd2, j);
+                const int kidx = kbase + 32 * j + lane;
+                active[u] = kidx < m;
+                W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
+                slot[u] = (uint32_t)kidx;
+                if (P.canonical) {
+                    const uint32_t bal = s_fwd[warp][j];
+                    const uint32_t fb = fwd_before + __popc(bal & lanemask_lt());
+                    const bool is_fwd = (bal >> lane) & 1;
+                    slot[u] = is_fwd ? fb : nfwd_total + ((uint32_t)kidx - fb);
+                    fwd_before += __popc(bal);
+                }
+                word[u] = kmer_to_word<W>(x, P, BRUTE);
             }
-            if (active) {
-                W word = kmer_to_word<W>(x, P, BRUTE);
-                if (MODE == 0) ow[slot] = word;
-                else of[slot] = probe_key<W, Suf, WB>(ix, P, word).found ? 1 : 0;
+            if (MODE == 0) {
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (active[u]) ow[slot[u]] = word[u];
+            } else {
+                // staged membership probe (index_view.cuh): every stage issues U independent loads
+                Suf s[U];
+                uint32_t k32[U], lo[U], hi[U], g[U];
+                bool present[U];
+                uint2 de[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    uint32_t prefix;
+                    split_key<W, Suf>(word[u], P, prefix, s[u]);
+                    k32[u] = key32<Suf>(s[u], P.suffix_bits);
+                    present[u] = active[u] && ix.nb != 0;
+                    lo[u] = prefix;
+                    de[u] = ldg_keep(ix.dir + (present[u] ? (prefix >> 5) : 0u));
+                }
+                uint2 range[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t bit = lo[u] & 31;
+                    const uint32_t rank = de[u].y + __popc(de[u].x & ((1u << bit) - 1u));
+                    present[u] = present[u] && ((de[u].x >> bit) & 1u);
+                    range[u] = ldg_keep(ix.bucket_range + (present[u] ? rank : 0u));
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    lo[u] = present[u] ? range[u].x : 0u;
+                    hi[u] = present[u] ? range[u].y : 0u;
+                    g[u] = lo[u] + predict_slot(ix.sub, lo[u], hi[u], k32[u]);
+                }
+                Suf e[U][WN];
+#pragma unroll
+                for (int u = 0; u < U; u++) load_window<Suf, WB>(ix.suf + (g[u] & ~(uint32_t)(WN - 1)), e[u]);
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    int r = 0;
+                    uint32_t L = lo[u], R = hi[u], gg = g[u];
+                    if (present[u]) r = eval_window<Suf, WB>(e[u], gg & ~(uint32_t)(WN - 1), s[u], k32[u], P.suffix_bits, R - L, L, R, gg);
+                    if (active[u] && r >= 0) s_flags[slot[u]] = (uint8_t)r;
+                    q_push(r < 0, s[u], L, R, gg, hi[u] - lo[u], slot[u]);
+                    while (q_count >= 32) q_drain();  // keeps the queue below 32 + 32 entries
+                }
             }
+        }
+        if (MODE == 1) {
+            while (q_count > 0) q_drain();
+            __syncthreads();
+            for (int i = threadIdx.x; i < m; i += SW_THREADS) of[i] = s_flags[i];
         }
         __syncthreads();  // s_piece / s_fwd reuse in the next grid-stride iteration
     }
