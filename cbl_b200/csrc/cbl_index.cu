@@ -129,6 +129,8 @@ public:
         if (!attr_done) {
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, ByteDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, ByteDigit<W>>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             attr_done = true;
         }
         CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -286,8 +288,8 @@ public:
         const int n_pass = (key_bits + 7) / 8;
         DevBuf<unsigned long long> hist((size_t)n_pass * 256, st_);
         hist.zero();
-        unsigned hgrid = (unsigned)std::min<uint64_t>(div_up(n, RS_THREADS * 16), 148 * 8);
-        CBL_LAUNCH((radix_hist_kernel<W>), hgrid, RS_THREADS, 0, st_, a, n, n_pass, hist.get());
+        unsigned hgrid = (unsigned)std::min<uint64_t>(div_up(n, RH_THREADS * RH_KEYS), 148 * 4);
+        CBL_LAUNCH((radix_hist_kernel<W>), hgrid, RH_THREADS, (size_t)n_pass * 256 * sizeof(uint32_t), st_, a, n, n_pass, hist.get());
         CBL_LAUNCH(radix_scan_hist_kernel, n_pass, 256, 0, st_, hist.get());
         const uint64_t tiles = div_up(n, RsTile<W>::TILE);
         DevBuf<uint32_t> status(tiles * 256, st_), counter(1, st_);
