@@ -11,6 +11,7 @@
 #include <mutex>
 
 #include "index_ops.cuh"
+#include "merge_ops.cuh"
 #include "radix_sort.cuh"
 #include "seq_words.cuh"
 
@@ -84,6 +85,7 @@ class Index final : public IIndex {
     DevBuf<uint2> dir_, bucket_range_;
     DevBuf<uint32_t> bucket_prefix_, bucket_off_;
     DevBuf<Suf> suf_;
+    bool use_merge_ = true;   // CBL_MUTATE=edits selects the first-generation probe/edit-list path (kept for A/B runs)
     DevBuf<int8_t> sub_;      // interpolation corrections for the membership probe, rebuilt lazily
     bool sub_valid_ = false;
     uint32_t nb_ = 0;
@@ -121,6 +123,7 @@ public:
         suf_.zero();
         sub_.alloc(4, st_);
         sub_.zero();
+        { const char* m = getenv("CBL_MUTATE"); use_merge_ = !(m && std::string(m) == "edits"); }
         batch_kmers_ = env_u64("CBL_BATCH_KMERS", sizeof(W) == 8 ? (1ull << 27) : (1ull << 26));
         if (batch_kmers_ > RS_MAX_KEYS) batch_kmers_ = RS_MAX_KEYS;
         if (batch_kmers_ < CHUNK_KMERS) batch_kmers_ = CHUNK_KMERS;
@@ -130,6 +133,10 @@ public:
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, ByteDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, ByteDigit<W>>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_OR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_AND>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_SUB>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_XOR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             attr_done = true;
         }
@@ -418,6 +425,78 @@ public:
         ns.changed = true;
     }
 
+    // ------------------------------------------------------------------------------------------
+    // mutation by one streaming merge (merge_ops.cuh): keys = sorted distinct words, op = MERGE_*
+    // ------------------------------------------------------------------------------------------
+    template <int OP> void launch_merge_apply(unsigned tiles, const IndexView<Suf>& v, const W* keys, uint64_t nk, const uint32_t* part_i,
+                                              const uint32_t* part_r, Suf* suf_out, uint32_t* cnt, uint64_t* status, uint32_t* counter,
+                                              unsigned long long* n_out) {
+        const size_t smem = (size_t)(MG_TILE + 2) * sizeof(W);
+        CBL_LAUNCH((merge_apply_kernel<W, Suf, OP>), tiles, MG_THREADS, smem, st_, v, P_, keys, nk, part_i, part_r, suf_out, cnt, status,
+                   counter, n_out);
+    }
+    void merge_new_state(const W* keys, uint64_t nk, int op, NewState& ns) {
+        ns.changed = false;
+        const uint64_t V = n_ + nk;
+        if (nk == 0 || (n_ == 0 && (op == MERGE_AND || op == MERGE_SUB))) {
+            if (op == MERGE_AND && n_ != 0) {  // A & {} = {}
+                ns.dir.alloc(n_dir_, st_); ns.dir.zero();
+                ns.bucket_range.alloc(1, st_); ns.bucket_prefix.alloc(1, st_); ns.bucket_off.alloc(1, st_); ns.bucket_off.zero();
+                ns.suf.alloc(SUF_PAD, st_);
+                ns.nb = 0; ns.n = 0; ns.last_prefix = 0; ns.changed = true;
+            }
+            return;
+        }
+        const IndexView<Suf> v = view();
+        const uint64_t tiles = div_up(V, MG_TILE);
+        DevBuf<uint32_t> part_i(tiles + 1, st_), part_r(tiles + 1, st_);
+        CBL_LAUNCH((merge_partition_kernel<W, Suf>), (unsigned)div_up(tiles + 1, 128), 128, 0, st_, v, P_, keys, nk, tiles, part_i.get(), part_r.get());
+        const uint64_t n_prefix = n_dir_ * 32;
+        DevBuf<uint32_t> cnt(n_prefix, st_);
+        cnt.zero();
+        const uint64_t cap = (op == MERGE_AND || op == MERGE_SUB) ? n_ : V;
+        ns.suf.alloc(cap + SUF_PAD, st_);
+        DevBuf<unsigned long long> totals(4, st_);
+        totals.zero();
+        {
+            Lookback lb(tiles, st_);
+            switch (op) {
+                case MERGE_OR: launch_merge_apply<MERGE_OR>((unsigned)tiles, v, keys, nk, part_i.get(), part_r.get(), ns.suf.get(), cnt.get(), lb.status.get(), lb.counter.get(), totals.get()); break;
+                case MERGE_AND: launch_merge_apply<MERGE_AND>((unsigned)tiles, v, keys, nk, part_i.get(), part_r.get(), ns.suf.get(), cnt.get(), lb.status.get(), lb.counter.get(), totals.get()); break;
+                case MERGE_SUB: launch_merge_apply<MERGE_SUB>((unsigned)tiles, v, keys, nk, part_i.get(), part_r.get(), ns.suf.get(), cnt.get(), lb.status.get(), lb.counter.get(), totals.get()); break;
+                default: launch_merge_apply<MERGE_XOR>((unsigned)tiles, v, keys, nk, part_i.get(), part_r.get(), ns.suf.get(), cnt.get(), lb.status.get(), lb.counter.get(), totals.get()); break;
+            }
+        }
+        ns.dir.alloc(n_dir_, st_);
+        DevBuf<uint32_t> word_off(n_dir_, st_);
+        {
+            const uint64_t t = div_up(n_dir_, 256);
+            Lookback lb_rank(t, st_), lb_off(t, st_);
+            CBL_LAUNCH(dir_bits_kernel, (unsigned)t, 256, 0, st_, cnt.get(), n_dir_, ns.dir.get(), word_off.get(), lb_rank.status.get(),
+                       lb_off.status.get(), lb_rank.counter.get(), totals.get() + 1);
+        }
+        unsigned long long h[3] = {0, 0, 0};  // merged element count, buckets, elements by the directory
+        CUDA_CHECK(cudaMemcpyAsync(h, totals.get(), sizeof h, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        const uint64_t n_new = h[0], nb_new = h[1];
+        if (h[2] != n_new)
+            throw Error(CBL_ECUDA, "internal: directory total " + std::to_string(h[2]) + " != element count " + std::to_string(n_new));
+        if (n_new >= (1ull << 32))
+            throw Error(CBL_EINVAL, "shard would hold >= 2^32 k-mers; bucket offsets are 32-bit — shard the index over more GPUs");
+        ns.bucket_prefix.alloc(nb_new ? nb_new : 1, st_);
+        ns.bucket_off.alloc(nb_new + 1, st_);
+        ns.bucket_range.alloc(nb_new ? nb_new : 1, st_);
+        CBL_LAUNCH(dir_fill_kernel, (unsigned)div_up(n_dir_, 256), 256, 0, st_, cnt.get(), ns.dir.get(), word_off.get(), n_dir_,
+                   ns.bucket_prefix.get(), ns.bucket_off.get(), ns.bucket_range.get(), (uint32_t)nb_new, (uint32_t)n_new);
+        uint32_t last = 0;
+        if (nb_new) CUDA_CHECK(cudaMemcpyAsync(&last, ns.bucket_prefix.get() + (nb_new - 1), 4, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        ns.nb = (uint32_t)nb_new;
+        ns.n = n_new;
+        ns.last_prefix = last;
+        ns.changed = true;
+    }
+
     // unsorted words in `a` (n of them, `b` same-size scratch) -> applied to this index
     void mutate_with_words(W* a, W* b, uint64_t n, int mode) {
         if (n == 0) return;
@@ -425,7 +504,8 @@ public:
         W* other = sorted == a ? b : a;
         uint64_t nu = unique_keys(sorted, n, other);
         NewState ns;
-        compute_new_state(other, nu, mode, view(), sorted, ns);
+        if (use_merge_) merge_new_state(other, nu, mode == EDIT_INS ? MERGE_OR : MERGE_SUB, ns);
+        else compute_new_state(other, nu, mode, view(), sorted, ns);
         if (ns.changed) adopt(ns);
     }
 
@@ -771,6 +851,13 @@ public:
     }
     void setop_new_state(int op, Index* o, NewState& ns) {
         o->sync();
+        if (use_merge_) {
+            if (o->n_ == 0 && op != SETOP_AND) { ns.changed = false; return; }
+            DevBuf<W> theirs(o->n_ ? o->n_ : 1, st_);
+            if (o->n_) CBL_LAUNCH((expand_kernel<W, Suf>), (unsigned)div_up(o->n_, OP_TILE), OP_THREADS, 0, st_, o->view(), P_, (uint64_t)0, o->n_, 0, theirs.get());
+            merge_new_state(theirs.get(), o->n_, op, ns);
+            return;
+        }
         if (op == SETOP_AND) {
             if (n_ == 0) { ns.changed = false; return; }
             DevBuf<W> mine(n_, st_);

@@ -1,0 +1,257 @@
+// Kernels k4-k7 (second generation): every mutation of a shard — insert_seq, remove_seq, | & - ^ — is ONE
+// streaming merge of two ascending word sequences:
+//     A = the resident index (CSR: prefix of the bucket, suffix of the element), never materialised as words
+//     B = the batch (sorted, distinct words; for set operations the other index expanded)
+// Replaces WordSet::insert_batch / remove_batch (src/wordset/mod.rs:187-237) and the binary set
+// operations (src/wordset/set_ops.rs:78-410, src/trievec/set_ops.rs:5-257, src/bitvector/set_ops.rs:4-106).
+//
+//   merge_partition_kernel  merge-path split points: tile t covers merged positions [t*TILE, (t+1)*TILE)
+//   merge_apply_kernel      per tile: stage A and B words in shared memory, per-thread merge-path split,
+//                           8-step serial merge with duplicate detection, emit by set-op rule, write new
+//                           suffixes (tile offsets by decoupled look-back) and add run lengths to the
+//                           dense per-prefix counters (one atomic per (tile, prefix) run)
+//   dir_bits_kernel         per-prefix counters -> bitvector + popcount rank directory (warp ballots,
+//                           block scan, look-back) and the element offset of every directory word
+//   dir_fill_kernel         bucket_prefix / bucket_off / bucket_range from the counters
+//
+// Traffic per mutation: N*S (old suffixes) + nB*W (batch) + N'*S (new suffixes) + 3 * 2^P * 4 (counters).
+#pragma once
+#include "index_view.cuh"
+
+namespace cbl {
+
+constexpr int MG_THREADS = 256;
+constexpr int MG_ITEMS = 8;
+constexpr int MG_TILE = MG_THREADS * MG_ITEMS;
+
+enum : int { MERGE_OR = 0, MERGE_AND = 1, MERGE_SUB = 2, MERGE_XOR = 3 };  // same numbering as SetOp
+
+// A[i] <= key ?   (A = the index seen as an ascending word sequence; i < ix.n, ix.nb > 0)
+template <class W, class Suf>
+__device__ __forceinline__ bool index_elem_le(const IndexView<Suf>& ix, const KParams& P, uint32_t i, W key) {
+    uint32_t prefix, rank;
+    Suf s;
+    split_key<W, Suf>(key, P, prefix, s);
+    const bool present = dir_test_rank(ix.dir, prefix, rank);
+    const uint32_t start = __ldg(ix.bucket_off + rank);  // first element whose prefix is >= key's prefix
+    if (i < start) return true;
+    if (!present) return false;
+    const uint32_t end = __ldg(ix.bucket_off + rank + 1);
+    if (i >= end) return false;
+    return ix.suf[i] <= s;
+}
+
+// part_i[t] = number of A elements among the first min(t * TILE, nA + nB) merged elements (A first on
+// ties); part_r[t] = rank of the bucket holding A[part_i[t]] (nb when part_i[t] == nA).  t in [0, tiles].
+template <class W, class Suf>
+__global__ void merge_partition_kernel(IndexView<Suf> ix, KParams P, const W* __restrict__ B, uint64_t nB, uint64_t tiles,
+                                       uint32_t* __restrict__ part_i, uint32_t* __restrict__ part_r) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > tiles) return;
+    const uint64_t nA = ix.n;
+    const uint64_t D = min(t * (uint64_t)MG_TILE, nA + nB);
+    uint64_t lo = D > nB ? D - nB : 0, hi = min(D, nA);
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (index_elem_le<W, Suf>(ix, P, (uint32_t)mid, B[D - 1 - mid])) lo = mid + 1; else hi = mid;
+    }
+    part_i[t] = (uint32_t)lo;
+    part_r[t] = lo < nA ? (uint32_t)(upper_bound_dev<uint32_t>(ix.bucket_off, (uint64_t)ix.nb + 1, (uint32_t)lo) - 1) : ix.nb;
+}
+
+template <class W, class Suf, int OP>
+__global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> ix, KParams P, const W* __restrict__ B, uint64_t nB,
+                                                                 const uint32_t* __restrict__ part_i, const uint32_t* __restrict__ part_r,
+                                                                 Suf* __restrict__ suf_out, uint32_t* __restrict__ prefix_cnt,
+                                                                 volatile uint64_t* status, uint32_t* tile_counter,
+                                                                 unsigned long long* __restrict__ n_out) {
+    extern __shared__ __align__(16) unsigned char mg_smem[];
+    W* sK = reinterpret_cast<W*>(mg_smem);                       // [0] A halo, [1, na] A, (na, na + nb] B, [na + nb + 1] B halo
+    uint32_t* s_pref = reinterpret_cast<uint32_t*>(mg_smem);     // reused after the merge: prefixes of the emitted elements
+    __shared__ uint8_t s_start[MG_TILE];
+    __shared__ uint16_t s_head[MG_TILE];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_excl;
+    __shared__ uint32_t s_tmp[33];
+    const W SENTINEL = ~(W)0;  // no word is all ones (the position field of an all-ones necklace is 0)
+
+    const uint32_t tile = block_ticket(tile_counter, &s_tile);
+    const uint64_t nA = ix.n;
+    const uint64_t D0 = min((uint64_t)tile * MG_TILE, nA + nB), D1 = min((uint64_t)(tile + 1) * MG_TILE, nA + nB);
+    const uint32_t i0 = part_i[tile], i1 = part_i[tile + 1];
+    const uint64_t j0 = D0 - i0, j1 = D1 - i1;
+    const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
+    const uint32_t r0 = part_r[tile], r1 = part_r[tile + 1];
+
+    // ---- stage A (suffix + prefix of its bucket) and B ----
+    for (int i = threadIdx.x; i < MG_TILE; i += MG_THREADS) s_start[i] = 0;
+    __syncthreads();
+    if (na > 0)
+        for (uint32_t r = r0 + 1 + threadIdx.x; r <= r1 && r < ix.nb; r += MG_THREADS) {
+            const uint32_t o = ix.bucket_off[r];
+            if (o < i1) s_start[o - i0] = 1;
+        }
+    __syncthreads();
+    {
+        const int s0 = threadIdx.x * MG_ITEMS;
+        uint32_t c = 0;
+#pragma unroll
+        for (int e = 0; e < MG_ITEMS; e++) c += s_start[s0 + e];
+        uint32_t total;
+        uint32_t rank = r0 + block_excl_scan<uint32_t, MG_THREADS>(c, s_tmp, total);
+#pragma unroll
+        for (int e = 0; e < MG_ITEMS; e++) {
+            const int s = s0 + e;
+            rank += s_start[s];
+            if (s < na) sK[1 + s] = (W)(((W)ix.bucket_prefix[rank] << P.suffix_bits) | (W)ix.suf[i0 + s]);
+        }
+        for (int s = threadIdx.x; s < nb; s += MG_THREADS) sK[1 + na + s] = B[j0 + s];
+        if (threadIdx.x == 0) {
+            W h = SENTINEL;
+            if (i0 > 0) {  // A[i0 - 1]: in bucket r0 unless that bucket starts exactly at i0
+                const uint32_t rp = (r0 < ix.nb && ix.bucket_off[r0] < i0) ? r0 : r0 - 1;
+                h = (W)(((W)ix.bucket_prefix[rp] << P.suffix_bits) | (W)ix.suf[i0 - 1]);
+            }
+            sK[0] = h;
+            sK[1 + na + nb] = j1 < nB ? B[j1] : SENTINEL;
+        }
+    }
+    __syncthreads();
+
+    // ---- per-thread merge-path split inside the tile, then MG_ITEMS serial steps ----
+    const W* sA = sK + 1;
+    const W* sB = sK + 1 + na;
+    const int d = min((int)threadIdx.x * MG_ITEMS, na + nb);
+    int lo = max(0, d - nb), hi = min(d, na);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sA[mid] <= sB[d - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    int ia = lo, ib = d - lo;
+    W out[MG_ITEMS];
+    uint32_t emit_mask = 0;
+#pragma unroll
+    for (int e = 0; e < MG_ITEMS; e++) {
+        out[e] = 0;
+        if (ia + ib < na + nb) {
+            const W a = ia < na ? sA[ia] : SENTINEL;  // (the B halo slot when ia == na is never compared as an A)
+            const W b = sB[ib];                        // ib == nb reads the B halo
+            const bool take_a = ia < na && (ib >= nb || a <= b);
+            bool emit;
+            if (take_a) {
+                const bool eq_b = b == a;              // b is the smallest B element >= a
+                emit = OP == MERGE_OR ? true : OP == MERGE_AND ? eq_b : !eq_b;
+                out[e] = a;
+                ia++;
+            } else {
+                const bool eq_a = sA[ia - 1] == b;     // the largest A element <= b (A halo when ia == 0)
+                emit = (OP == MERGE_OR || OP == MERGE_XOR) && !eq_a;
+                out[e] = b;
+                ib++;
+            }
+            emit_mask |= (emit ? 1u : 0u) << e;
+        }
+    }
+    const uint32_t cnt = __popc(emit_mask);
+    uint32_t tile_emitted;
+    const uint32_t off = block_excl_scan<uint32_t, MG_THREADS>(cnt, s_tmp, tile_emitted);
+    const uint64_t excl = block_lookback(status, tile, tile_emitted, &s_excl);  // (ends with __syncthreads: sK is dead)
+
+    // ---- write the new suffixes; publish the emitted prefixes for the run-length pass ----
+    {
+        uint32_t k = off;
+#pragma unroll
+        for (int e = 0; e < MG_ITEMS; e++)
+            if ((emit_mask >> e) & 1u) {
+                suf_out[excl + k] = (Suf)(out[e] & low_mask<W>(P.suffix_bits));
+                s_pref[k] = (uint32_t)(out[e] >> P.suffix_bits);
+                k++;
+            }
+    }
+    __syncthreads();
+    // heads of prefix runs inside the tile -> one atomic per run
+    {
+        uint32_t hm = 0, k = off;
+#pragma unroll
+        for (int e = 0; e < MG_ITEMS; e++)
+            if ((emit_mask >> e) & 1u) {
+                if (k == 0 || s_pref[k] != s_pref[k - 1]) hm |= 1u << e;
+                k++;
+            }
+        uint32_t n_heads;
+        uint32_t hoff = block_excl_scan<uint32_t, MG_THREADS>(__popc(hm), s_tmp, n_heads);
+        k = off;
+#pragma unroll
+        for (int e = 0; e < MG_ITEMS; e++)
+            if ((emit_mask >> e) & 1u) {
+                if ((hm >> e) & 1u) s_head[hoff++] = (uint16_t)k;
+                k++;
+            }
+        __syncthreads();
+        for (uint32_t h = threadIdx.x; h < n_heads; h += MG_THREADS) {
+            const uint32_t p0 = s_head[h], p1 = h + 1 < n_heads ? s_head[h + 1] : tile_emitted;
+            atomicAdd(prefix_cnt + s_pref[p0], p1 - p0);
+        }
+    }
+    if (threadIdx.x == 0 && D1 == nA + nB) *n_out = excl + tile_emitted;
+}
+
+// Dense per-prefix counters -> directory.  One warp handles 32 directory words (1024 prefixes):
+// coalesced counter rows, ballots give the bit words, warp sums the element counts.
+// dir[w] = {bits, rank}; word_off[w] = number of elements in prefixes below 32 * w; totals[0] = nb, totals[1] = n.
+__global__ void __launch_bounds__(256) dir_bits_kernel(const uint32_t* __restrict__ prefix_cnt, uint64_t n_words, uint2* __restrict__ dir,
+                                                       uint32_t* __restrict__ word_off, volatile uint64_t* status_rank,
+                                                       volatile uint64_t* status_off, uint32_t* tile_counter,
+                                                       unsigned long long* __restrict__ totals) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_excl;
+    __shared__ uint32_t s_tmp[33];
+    const uint32_t tile = block_ticket(tile_counter, &s_tile);
+    const int lane = threadIdx.x & 31;
+    const uint64_t w = (uint64_t)tile * 256 + threadIdx.x;                   // this thread's directory word
+    const uint64_t row0 = ((uint64_t)tile * 256 + (threadIdx.x & ~31)) * 32;  // first prefix of the warp's 32 words
+    uint32_t bits = 0, sum = 0;
+    for (int r = 0; r < 32; r++) {
+        const uint64_t wr = (uint64_t)tile * 256 + (threadIdx.x & ~31) + r;
+        const uint32_t v = wr < n_words ? prefix_cnt[row0 + (uint64_t)r * 32 + lane] : 0u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, v != 0);
+        const uint32_t sm = warp_sum(v);
+        if (lane == r) { bits = bal; sum = sm; }
+    }
+    uint32_t tot_bits, tot_sum;
+    const uint32_t rk = block_excl_scan<uint32_t, 256>(__popc(bits), s_tmp, tot_bits);
+    const uint32_t of = block_excl_scan<uint32_t, 256>(sum, s_tmp, tot_sum);
+    const uint64_t ex_rank = block_lookback(status_rank, tile, tot_bits, &s_excl);
+    const uint64_t ex_off = block_lookback(status_off, tile, tot_sum, &s_excl);
+    if (w < n_words) {
+        dir[w] = make_uint2(bits, (uint32_t)ex_rank + rk);
+        word_off[w] = (uint32_t)ex_off + of;
+    }
+    if (threadIdx.x == 0 && (uint64_t)(tile + 1) * 256 >= n_words && (uint64_t)tile * 256 < n_words) {
+        totals[0] = ex_rank + tot_bits;
+        totals[1] = ex_off + tot_sum;
+    }
+}
+
+// bucket_prefix / bucket_off / bucket_range of every occupied prefix (thread = directory word)
+__global__ void dir_fill_kernel(const uint32_t* __restrict__ prefix_cnt, const uint2* __restrict__ dir, const uint32_t* __restrict__ word_off,
+                                uint64_t n_words, uint32_t* __restrict__ bucket_prefix, uint32_t* __restrict__ bucket_off,
+                                uint2* __restrict__ bucket_range, uint32_t nb, uint32_t n) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w == 0) bucket_off[nb] = n;
+    if (w >= n_words) return;
+    const uint2 e = dir[w];
+    uint32_t bits = e.x, r = e.y, o = word_off[w];
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t p = (uint32_t)(w * 32 + b), c = prefix_cnt[p];
+        bucket_prefix[r] = p;
+        bucket_off[r] = o;
+        bucket_range[r] = make_uint2(o, o + c);
+        o += c;
+        r++;
+    }
+}
+
+}  // namespace cbl
