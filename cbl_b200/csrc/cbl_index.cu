@@ -4,6 +4,7 @@
 #include "cbl_index.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdlib>
 #include <cstring>
@@ -59,6 +60,21 @@ static int pos_bits_for(int kmer_bits) {  // src/cbl.rs:66
     while ((1 << p) < kmer_bits) p++;
     return p;
 }
+
+// CBL_TRACE=1: host-side timeline of a mutation on stderr (developer aid)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    cudaStream_t s;
+    explicit Trace(cudaStream_t st) : on(getenv("CBL_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), s(st) {}
+    void mark(const char* what, bool sync = false) {
+        if (!on) return;
+        if (sync) cudaStreamSynchronize(s);
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cbl trace] %-28s %9.3f ms%s\n", what, std::chrono::duration<double, std::milli>(t - t0).count(), sync ? " (synced)" : "");
+        t0 = std::chrono::steady_clock::now();
+    }
+};
 
 static uint64_t env_u64(const char* name, uint64_t dflt) {
     const char* v = getenv(name);
@@ -428,10 +444,16 @@ public:
     // ------------------------------------------------------------------------------------------
     // mutation by one streaming merge (merge_ops.cuh): keys = sorted distinct words, op = MERGE_*
     // ------------------------------------------------------------------------------------------
+    static uint64_t round_capacity(uint64_t n) {
+        if (n < (1u << 20)) return n;
+        int top = 63 - __builtin_clzll(n);
+        const uint64_t step = 1ull << (top - 2);
+        return (n + step - 1) / step * step;
+    }
     template <int OP> void launch_merge_apply(unsigned tiles, const IndexView<Suf>& v, const W* keys, uint64_t nk, const uint32_t* part_i,
                                               const uint32_t* part_r, Suf* suf_out, uint32_t* cnt, uint64_t* status, uint32_t* counter,
                                               unsigned long long* n_out) {
-        const size_t smem = (size_t)(MG_TILE + 2) * sizeof(W);
+        const size_t smem = (size_t)MG_SMEM_ELEMS * sizeof(W);
         CBL_LAUNCH((merge_apply_kernel<W, Suf, OP>), tiles, MG_THREADS, smem, st_, v, P_, keys, nk, part_i, part_r, suf_out, cnt, status,
                    counter, n_out);
     }
@@ -454,7 +476,9 @@ public:
         const uint64_t n_prefix = n_dir_ * 32;
         DevBuf<uint32_t> cnt(n_prefix, st_);
         cnt.zero();
-        const uint64_t cap = (op == MERGE_AND || op == MERGE_SUB) ? n_ : V;
+        // capacity is rounded up to 4 steps per octave so that the blocks freed by earlier, smaller states of a
+        // growing index can be reused by the memory pool instead of a fresh driver allocation per batch
+        const uint64_t cap = round_capacity((op == MERGE_AND || op == MERGE_SUB) ? n_ : V);
         ns.suf.alloc(cap + SUF_PAD, st_);
         DevBuf<unsigned long long> totals(4, st_);
         totals.zero();
@@ -500,13 +524,18 @@ public:
     // unsorted words in `a` (n of them, `b` same-size scratch) -> applied to this index
     void mutate_with_words(W* a, W* b, uint64_t n, int mode) {
         if (n == 0) return;
+        Trace tr(st_);
         W* sorted = sort_keys(a, b, n);
+        tr.mark("  sort enqueue");
         W* other = sorted == a ? b : a;
         uint64_t nu = unique_keys(sorted, n, other);
+        tr.mark("  unique (sync inside)");
         NewState ns;
         if (use_merge_) merge_new_state(other, nu, mode == EDIT_INS ? MERGE_OR : MERGE_SUB, ns);
         else compute_new_state(other, nu, mode, view(), sorted, ns);
+        tr.mark("  new state (syncs inside)");
         if (ns.changed) adopt(ns);
+        tr.mark("  adopt");
     }
 
     // ------------------------------------------------------------------------------------------
@@ -523,11 +552,16 @@ public:
             size_t q = p;
             uint64_t nk = 0;
             while (q < np && (q == p || nk + pl.kmers[q] <= batch_kmers_)) { nk += pl.kmers[q]; q++; }
+            Trace tr(st_);
             DevPieces dp;
             upload_pieces(pl, p, q, pl.out_off[p], d_seq, n_bytes, dp, st_);
+            tr.mark("upload pieces");
             DevBuf<W> a(nk, st_), b(nk, st_);
+            tr.mark("alloc a,b");
             run_seq_words(dp.batch, 0, false, a.get(), nullptr, st_);
+            tr.mark("seq_words (sync inside)");
             mutate_with_words(a.get(), b.get(), nk, mode);
+            tr.mark("mutate_with_words", true);
             p = q;
         }
         CUDA_CHECK(cudaStreamSynchronize(st_));

@@ -59,6 +59,11 @@ __global__ void merge_partition_kernel(IndexView<Suf> ix, KParams P, const W* __
     part_r[t] = lo < nA ? (uint32_t)(upper_bound_dev<uint32_t>(ix.bucket_off, (uint64_t)ix.nb + 1, (uint32_t)lo) - 1) : ix.nb;
 }
 
+// shared-memory slot of output element k: one pad word per 32 elements makes the "8 consecutive elements
+// per thread" write pattern bank-conflict free while keeping the sequential read-out conflict free
+__device__ __forceinline__ uint32_t mg_pad(uint32_t k) { return k + (k >> 5); }
+constexpr int MG_SMEM_ELEMS = MG_TILE + 2 + MG_TILE / 32 + 2;   // staging words (also holds the padded output)
+
 template <class W, class Suf, int OP>
 __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> ix, KParams P, const W* __restrict__ B, uint64_t nB,
                                                                  const uint32_t* __restrict__ part_i, const uint32_t* __restrict__ part_r,
@@ -66,14 +71,16 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
                                                                  volatile uint64_t* status, uint32_t* tile_counter,
                                                                  unsigned long long* __restrict__ n_out) {
     extern __shared__ __align__(16) unsigned char mg_smem[];
-    W* sK = reinterpret_cast<W*>(mg_smem);                       // [0] A halo, [1, na] A, (na, na + nb] B, [na + nb + 1] B halo
-    uint32_t* s_pref = reinterpret_cast<uint32_t*>(mg_smem);     // reused after the merge: prefixes of the emitted elements
-    __shared__ uint8_t s_start[MG_TILE];
-    __shared__ uint16_t s_head[MG_TILE];
+    W* sK = reinterpret_cast<W*>(mg_smem);                 // [0] A halo, [1, na] A, (na, na + nb] B, [na + nb + 1] B halo
+    Suf* s_out = reinterpret_cast<Suf*>(mg_smem);          // after the merge: emitted suffixes (padded slots)
+    __shared__ uint16_t s_pos[MG_TILE + 1];                // first: bucket starts inside the tile; later: run heads
+    __shared__ uint32_t s_pfx[MG_TILE + 1];                // first: prefix of those buckets;       later: prefix of the heads
+    __shared__ uint32_t s_last[MG_THREADS / 32];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_excl;
     __shared__ uint32_t s_tmp[33];
     const W SENTINEL = ~(W)0;  // no word is all ones (the position field of an all-ones necklace is 0)
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
 
     const uint32_t tile = block_ticket(tile_counter, &s_tile);
     const uint64_t nA = ix.n;
@@ -83,38 +90,36 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
     const uint32_t r0 = part_r[tile], r1 = part_r[tile + 1];
 
-    // ---- stage A (suffix + prefix of its bucket) and B ----
-    for (int i = threadIdx.x; i < MG_TILE; i += MG_THREADS) s_start[i] = 0;
+    // ---- buckets of the A range: entry 0 = the bucket holding A[i0], then every bucket starting inside (i0, i1) ----
+    int n_bk = 0;
+    if (na > 0) {
+        const uint32_t r_hi = min(r1, ix.nb - 1);             // last candidate rank
+        n_bk = (int)(r_hi - r0) + 1;
+        if (r_hi > r0 && ix.bucket_off[r_hi] >= i1) n_bk--;   // the bucket of A[i1] starts exactly at i1
+        for (int j = threadIdx.x; j < n_bk; j += MG_THREADS) {
+            s_pos[j] = j == 0 ? 0 : (uint16_t)(ix.bucket_off[r0 + j] - i0);
+            s_pfx[j] = ix.bucket_prefix[r0 + j];
+        }
+    }
     __syncthreads();
-    if (na > 0)
-        for (uint32_t r = r0 + 1 + threadIdx.x; r <= r1 && r < ix.nb; r += MG_THREADS) {
-            const uint32_t o = ix.bucket_off[r];
-            if (o < i1) s_start[o - i0] = 1;
+    // ---- stage A words and B words (coalesced global reads, consecutive shared slots) ----
+    for (int s = threadIdx.x; s < na; s += MG_THREADS) {
+        int lo = 0, hi = n_bk;                                 // last bucket with start <= s
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)s_pos[mid] <= s) lo = mid; else hi = mid;
         }
-    __syncthreads();
-    {
-        const int s0 = threadIdx.x * MG_ITEMS;
-        uint32_t c = 0;
-#pragma unroll
-        for (int e = 0; e < MG_ITEMS; e++) c += s_start[s0 + e];
-        uint32_t total;
-        uint32_t rank = r0 + block_excl_scan<uint32_t, MG_THREADS>(c, s_tmp, total);
-#pragma unroll
-        for (int e = 0; e < MG_ITEMS; e++) {
-            const int s = s0 + e;
-            rank += s_start[s];
-            if (s < na) sK[1 + s] = (W)(((W)ix.bucket_prefix[rank] << P.suffix_bits) | (W)ix.suf[i0 + s]);
+        sK[1 + s] = (W)(((W)s_pfx[lo] << P.suffix_bits) | (W)ix.suf[i0 + s]);
+    }
+    for (int s = threadIdx.x; s < nb; s += MG_THREADS) sK[1 + na + s] = B[j0 + s];
+    if (threadIdx.x == 0) {
+        W h = SENTINEL;
+        if (i0 > 0) {  // A[i0 - 1]: in bucket r0 unless that bucket starts exactly at i0
+            const uint32_t rp = (r0 < ix.nb && ix.bucket_off[r0] < i0) ? r0 : r0 - 1;
+            h = (W)(((W)ix.bucket_prefix[rp] << P.suffix_bits) | (W)ix.suf[i0 - 1]);
         }
-        for (int s = threadIdx.x; s < nb; s += MG_THREADS) sK[1 + na + s] = B[j0 + s];
-        if (threadIdx.x == 0) {
-            W h = SENTINEL;
-            if (i0 > 0) {  // A[i0 - 1]: in bucket r0 unless that bucket starts exactly at i0
-                const uint32_t rp = (r0 < ix.nb && ix.bucket_off[r0] < i0) ? r0 : r0 - 1;
-                h = (W)(((W)ix.bucket_prefix[rp] << P.suffix_bits) | (W)ix.suf[i0 - 1]);
-            }
-            sK[0] = h;
-            sK[1 + na + nb] = j1 < nB ? B[j1] : SENTINEL;
-        }
+        sK[0] = h;
+        sK[1 + na + nb] = j1 < nB ? B[j1] : SENTINEL;
     }
     __syncthreads();
 
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     for (int e = 0; e < MG_ITEMS; e++) {
         out[e] = 0;
         if (ia + ib < na + nb) {
-            const W a = ia < na ? sA[ia] : SENTINEL;  // (the B halo slot when ia == na is never compared as an A)
+            const W a = ia < na ? sA[ia] : SENTINEL;
             const W b = sB[ib];                        // ib == nb reads the B halo
             const bool take_a = ia < na && (ib >= nb || a <= b);
             bool emit;
@@ -152,46 +157,51 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
             emit_mask |= (emit ? 1u : 0u) << e;
         }
     }
-    const uint32_t cnt = __popc(emit_mask);
-    uint32_t tile_emitted;
-    const uint32_t off = block_excl_scan<uint32_t, MG_THREADS>(cnt, s_tmp, tile_emitted);
-    const uint64_t excl = block_lookback(status, tile, tile_emitted, &s_excl);  // (ends with __syncthreads: sK is dead)
-
-    // ---- write the new suffixes; publish the emitted prefixes for the run-length pass ----
+    // ---- prefix runs: a head is an emitted element whose prefix differs from the previously emitted one ----
+    uint32_t last = NONE;
+#pragma unroll
+    for (int e = 0; e < MG_ITEMS; e++)
+        if ((emit_mask >> e) & 1u) last = (uint32_t)(out[e] >> P.suffix_bits);
+    // prev = prefix of the element emitted last before this thread's range ("last defined value" scan)
+    uint32_t incl = last;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, dd);
+        if ((int)lane_id() >= dd && incl == NONE) incl = t;
+    }
+    uint32_t prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane_id() == 0) prev = NONE;
+    if (lane_id() == 31) s_last[threadIdx.x >> 5] = incl;
+    __syncthreads();   // also: every thread is done reading sK
+    for (int w = (int)(threadIdx.x >> 5) - 1; w >= 0 && prev == NONE; w--) prev = s_last[w];
+    uint32_t hm = 0;
+#pragma unroll
+    for (int e = 0; e < MG_ITEMS; e++)
+        if ((emit_mask >> e) & 1u) {
+            const uint32_t p = (uint32_t)(out[e] >> P.suffix_bits);
+            if (p != prev) hm |= 1u << e;
+            prev = p;
+        }
+    uint32_t packed_tot;
+    const uint32_t packed = block_excl_scan<uint32_t, MG_THREADS>(__popc(emit_mask) | (__popc(hm) << 16), s_tmp, packed_tot);
+    const uint32_t off = packed & 0xFFFFu, tile_emitted = packed_tot & 0xFFFFu, n_heads = packed_tot >> 16;
+    uint32_t hoff = packed >> 16;
+    const uint64_t excl = block_lookback(status, tile, tile_emitted, &s_excl);
     {
         uint32_t k = off;
 #pragma unroll
         for (int e = 0; e < MG_ITEMS; e++)
             if ((emit_mask >> e) & 1u) {
-                suf_out[excl + k] = (Suf)(out[e] & low_mask<W>(P.suffix_bits));
-                s_pref[k] = (uint32_t)(out[e] >> P.suffix_bits);
+                s_out[mg_pad(k)] = (Suf)(out[e] & low_mask<W>(P.suffix_bits));
+                if ((hm >> e) & 1u) { s_pos[hoff] = (uint16_t)k; s_pfx[hoff] = (uint32_t)(out[e] >> P.suffix_bits); hoff++; }
                 k++;
             }
     }
     __syncthreads();
-    // heads of prefix runs inside the tile -> one atomic per run
-    {
-        uint32_t hm = 0, k = off;
-#pragma unroll
-        for (int e = 0; e < MG_ITEMS; e++)
-            if ((emit_mask >> e) & 1u) {
-                if (k == 0 || s_pref[k] != s_pref[k - 1]) hm |= 1u << e;
-                k++;
-            }
-        uint32_t n_heads;
-        uint32_t hoff = block_excl_scan<uint32_t, MG_THREADS>(__popc(hm), s_tmp, n_heads);
-        k = off;
-#pragma unroll
-        for (int e = 0; e < MG_ITEMS; e++)
-            if ((emit_mask >> e) & 1u) {
-                if ((hm >> e) & 1u) s_head[hoff++] = (uint16_t)k;
-                k++;
-            }
-        __syncthreads();
-        for (uint32_t h = threadIdx.x; h < n_heads; h += MG_THREADS) {
-            const uint32_t p0 = s_head[h], p1 = h + 1 < n_heads ? s_head[h + 1] : tile_emitted;
-            atomicAdd(prefix_cnt + s_pref[p0], p1 - p0);
-        }
+    for (uint32_t k = threadIdx.x; k < tile_emitted; k += MG_THREADS) suf_out[excl + k] = s_out[mg_pad(k)];
+    for (uint32_t h = threadIdx.x; h < n_heads; h += MG_THREADS) {
+        const uint32_t p0 = s_pos[h], p1 = h + 1 < n_heads ? s_pos[h + 1] : tile_emitted;
+        atomicAdd(prefix_cnt + s_pfx[h], p1 - p0);
     }
     if (threadIdx.x == 0 && D1 == nA + nB) *n_out = excl + tile_emitted;
 }

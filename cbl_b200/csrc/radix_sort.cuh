@@ -164,9 +164,13 @@ __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kern
             if ((int)((info[i - 2] >> 11) & 31u) == lane) M2[digit(key[i - 2])] = 0;
         }
         const uint32_t d = digit(key[i]);
+#if CBL_RS_ABLATE == 2
+        const unsigned peers = 1u << lane;
+#else
         if (valid) atomicOr(&M[d], 1u << lane);
         __syncwarp();
         const unsigned peers = valid ? M[d] : (1u << lane);
+#endif
         info[i] = __popc(peers & lanemask_lt()) | (__popc(peers) << 5) | ((31 - __clz(peers)) << 11);
     }
     // 3. leaders reserve their group's slots in the warp histogram (in item order)
@@ -194,7 +198,10 @@ __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kern
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) { const uint32_t c = s_whist[w][t]; s_whist[w][t] = acc; acc += c; }   // slot of (warp, digit) in the tile
         uint32_t excl = 0;
-        if (tile > 0) {
+#ifndef CBL_RS_ABLATE
+#define CBL_RS_ABLATE 0
+#endif
+        if (tile > 0 && CBL_RS_ABLATE != 1) {
             for (long long prev = (long long)tile - 1; prev >= 0; prev--) {
                 uint32_t s;
                 do { s = status[(size_t)prev * 256 + t]; } while ((s >> 30) == 0);
