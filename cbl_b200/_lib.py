@@ -59,6 +59,13 @@ SIGNATURES = {
     "cbl_export_words_dev": (C.c_int32, [vp, C.c_uint64, C.c_uint64, vp]),
     "cbl_route_words_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, vp, vp, u64p]),
     "cbl_gather_u8_dev": (C.c_int32, [vp, vp, vp, C.c_size_t, vp]),
+    "cbl_peer_alloc": (C.c_int32, [vp, C.c_size_t, vpp, vp]),
+    "cbl_peer_open": (C.c_int32, [vp, vp, vpp]),
+    "cbl_peer_close": (C.c_int32, [vp, vp]),
+    "cbl_peer_free": (C.c_int32, [vp, vp]),
+    "cbl_route_counts_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, u64p]),
+    "cbl_route_scatter_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, vpp, u64p, u64p, vp]),
+    "cbl_probe_words_scatter_dev": (C.c_int32, [vp, vp, C.c_size_t, C.c_uint32, u64p, vpp, u64p]),
     "cbl_word_bytes": (C.c_int32, [vp, i32p]),
     "cbl_suffix_bits": (C.c_int32, [vp, i32p]),
     "cbl_seq_words": (C.c_int32, [vp, vp, u64p, C.c_size_t, u64p, u64p, C.c_int32]),

@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import u8p, u32p, u64p
+from ._lib import vpp as vpp_t
 
 Seq = Union[bytes, bytearray, memoryview, np.ndarray]
 
@@ -202,6 +203,50 @@ class CBL:
         counts = np.zeros(len(sp) + 1, dtype=np.uint64)
         self._chk(self._L.cbl_route_words_dev(self._h, d_words, n, sp.ctypes.data_as(u32p), len(sp), d_send, d_pos, counts.ctypes.data_as(u64p)))
         return counts
+
+    # -- fused route + exchange over peer memory (include/cbl_gpu.h) ------------------------------
+    IPC_HANDLE_BYTES = 64
+
+    def peer_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte CUDA IPC handle) of a block other processes of the box can map."""
+        p = C.c_void_p()
+        hb = (C.c_uint8 * self.IPC_HANDLE_BYTES)()
+        self._chk(self._L.cbl_peer_alloc(self._h, nbytes, C.byref(p), C.cast(hb, C.c_void_p)))
+        return int(p.value), bytes(hb)
+
+    def peer_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        hb = (C.c_uint8 * self.IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        self._chk(self._L.cbl_peer_open(self._h, C.cast(hb, C.c_void_p), C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, ptr: int) -> None:
+        self._chk(self._L.cbl_peer_close(self._h, ptr))
+
+    def peer_free(self, ptr: int) -> None:
+        self._chk(self._L.cbl_peer_free(self._h, ptr))
+
+    def route_counts_dev(self, d_words: int, n: int, splitters: np.ndarray) -> np.ndarray:
+        sp = np.ascontiguousarray(splitters, dtype=np.uint32)
+        counts = np.zeros(len(sp) + 1, dtype=np.uint64)
+        self._chk(self._L.cbl_route_counts_dev(self._h, d_words, n, sp.ctypes.data_as(u32p), len(sp), counts.ctypes.data_as(u64p)))
+        return counts
+
+    def route_scatter_dev(self, d_words: int, n: int, splitters: np.ndarray, peer_recv, recv_offset, counts, d_pos: int = 0) -> None:
+        sp = np.ascontiguousarray(splitters, dtype=np.uint32)
+        g = len(sp) + 1
+        ptrs = (C.c_void_p * g)(*[int(x) for x in peer_recv])
+        ro = np.ascontiguousarray(recv_offset, dtype=np.uint64)
+        ct = np.ascontiguousarray(counts, dtype=np.uint64)
+        self._chk(self._L.cbl_route_scatter_dev(self._h, d_words, n, sp.ctypes.data_as(u32p), len(sp), C.cast(ptrs, vpp_t), ro.ctypes.data_as(u64p),
+                                                ct.ctypes.data_as(u64p), d_pos))
+
+    def probe_words_scatter_dev(self, d_words: int, n: int, src_begin, peer_back, back_offset) -> None:
+        sb = np.ascontiguousarray(src_begin, dtype=np.uint64)
+        g = len(sb) - 1
+        ptrs = (C.c_void_p * g)(*[int(x) for x in peer_back])
+        bo = np.ascontiguousarray(back_offset, dtype=np.uint64)
+        self._chk(self._L.cbl_probe_words_scatter_dev(self._h, d_words, n, g, sb.ctypes.data_as(u64p), C.cast(ptrs, vpp_t), bo.ctypes.data_as(u64p)))
 
     def gather_u8_dev(self, d_src: int, d_pos: int, n: int, d_out: int) -> None:
         self._chk(self._L.cbl_gather_u8_dev(self._h, d_src, d_pos, n, d_out))

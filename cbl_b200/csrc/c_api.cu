@@ -400,6 +400,63 @@ int32_t cbl_gather_u8_dev(cbl_t* h, const uint8_t* d_src, const uint32_t* d_pos,
         h->ix->gather_u8_dev(d_src, d_pos, n, d_out);
     });
 }
+int32_t cbl_route_counts_dev(cbl_t* h, const void* d_words, size_t n, const uint32_t* splitters, uint32_t n_splitters, uint64_t* counts) {
+    return guard(h, [&] {
+        need(h, "handle"); need(counts, "counts");
+        if (n_splitters) need(splitters, "splitters");
+        if (n) need(d_words, "d_words");
+        h->ix->route_counts_dev(d_words, n, splitters, n_splitters, counts);
+    });
+}
+int32_t cbl_route_scatter_dev(cbl_t* h, const void* d_words, size_t n, const uint32_t* splitters, uint32_t n_splitters,
+                              void* const* peer_recv, const uint64_t* recv_offset, const uint64_t* counts, uint32_t* d_pos) {
+    return guard(h, [&] {
+        need(h, "handle"); need(peer_recv, "peer_recv"); need(recv_offset, "recv_offset"); need(counts, "counts");
+        if (n_splitters) need(splitters, "splitters");
+        if (n) need(d_words, "d_words");
+        h->ix->route_scatter_dev(d_words, n, splitters, n_splitters, peer_recv, recv_offset, counts, d_pos);
+    });
+}
+int32_t cbl_probe_words_scatter_dev(cbl_t* h, const void* d_words, size_t n, uint32_t n_src, const uint64_t* src_begin,
+                                    uint8_t* const* peer_back, const uint64_t* back_offset) {
+    return guard(h, [&] {
+        need(h, "handle"); need(src_begin, "src_begin"); need(peer_back, "peer_back"); need(back_offset, "back_offset");
+        if (n) need(d_words, "d_words");
+        h->ix->probe_words_scatter_dev(d_words, n, n_src, src_begin, peer_back, back_offset);
+    });
+}
+// ---- peer memory: plain cudaMalloc blocks shared between the processes of one box with CUDA IPC ----
+int32_t cbl_peer_alloc(cbl_t* h, size_t bytes, void** d_ptr, uint8_t* handle) {
+    return guard(h, [&] {
+        need(h, "handle"); need(d_ptr, "d_ptr"); need(handle, "handle bytes");
+        static_assert(sizeof(cudaIpcMemHandle_t) == CBL_IPC_HANDLE_BYTES, "IPC handle size");
+        CUDA_CHECK(cudaSetDevice(h->ix->config().device));
+        void* p = nullptr;
+        CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));
+        cudaIpcMemHandle_t mh;
+        cudaError_t e = cudaIpcGetMemHandle(&mh, p);
+        if (e != cudaSuccess) { cudaFree(p); CUDA_CHECK(e); }
+        memcpy(handle, &mh, sizeof mh);
+        *d_ptr = p;
+    });
+}
+int32_t cbl_peer_open(cbl_t* h, const uint8_t* handle, void** d_ptr) {
+    return guard(h, [&] {
+        need(h, "handle"); need(d_ptr, "d_ptr"); need(handle, "handle bytes");
+        CUDA_CHECK(cudaSetDevice(h->ix->config().device));
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handle, sizeof mh);
+        void* p = nullptr;
+        CUDA_CHECK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        *d_ptr = p;
+    });
+}
+int32_t cbl_peer_close(cbl_t* h, void* d_ptr) {
+    return guard(h, [&] { need(h, "handle"); CUDA_CHECK(cudaSetDevice(h->ix->config().device)); if (d_ptr) CUDA_CHECK(cudaIpcCloseMemHandle(d_ptr)); });
+}
+int32_t cbl_peer_free(cbl_t* h, void* d_ptr) {
+    return guard(h, [&] { need(h, "handle"); CUDA_CHECK(cudaSetDevice(h->ix->config().device)); if (d_ptr) CUDA_CHECK(cudaFree(d_ptr)); });
+}
 int32_t cbl_word_bytes(const cbl_t* h, int32_t* out) {
     return guard(mut(h), [&] {
         need(h, "handle"); need(out, "out");

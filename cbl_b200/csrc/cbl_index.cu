@@ -154,6 +154,8 @@ public:
             CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_SUB>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_XOR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             attr_done = true;
         }
         CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -811,14 +813,10 @@ public:
     void route_words_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* d_send, uint32_t* d_pos,
                          uint64_t* counts) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
-        if (n_split > ROUTE_MAX_SPLIT) throw Error(CBL_EINVAL, "too many splitters");
+        const DestDigit<W> dg = make_dest_digit(splitters, n_split);
         for (uint32_t i = 0; i <= n_split; i++) counts[i] = 0;
         if (n == 0) return;
         if (n > RS_MAX_KEYS) throw Error(CBL_EINVAL, "route batch too large (max 2^30 - 1 words per call)");
-        DestDigit<W> dg;
-        dg.suffix_bits = P_.suffix_bits;
-        dg.n_split = n_split;
-        for (int i = 0; i < ROUTE_MAX_SPLIT; i++) dg.split[i] = i < (int)n_split ? splitters[i] : 0xFFFFFFFFu;
         DevBuf<unsigned long long> hist(256, st_);
         hist.zero();
         unsigned hgrid = (unsigned)std::min<uint64_t>(div_up(n, 256 * 8), 148 * 16);
@@ -834,6 +832,73 @@ public:
                    (W*)d_send, nullptr, nullptr, n, dg, hist.get(), status.get(), counter.get(), d_pos);
         CUDA_CHECK(cudaStreamSynchronize(st_));
         for (uint32_t i = 0; i <= n_split; i++) counts[i] = h[i];
+    }
+    DestDigit<W> make_dest_digit(const uint32_t* splitters, uint32_t n_split) const {
+        if (n_split > ROUTE_MAX_SPLIT) throw Error(CBL_EINVAL, "too many splitters");
+        DestDigit<W> dg;
+        dg.suffix_bits = P_.suffix_bits;
+        dg.n_split = n_split;
+        for (int i = 0; i < ROUTE_MAX_SPLIT; i++) dg.split[i] = i < (int)n_split ? splitters[i] : 0xFFFFFFFFu;
+        return dg;
+    }
+    void route_counts_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, uint64_t* counts) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        const DestDigit<W> dg = make_dest_digit(splitters, n_split);
+        for (uint32_t i = 0; i <= n_split; i++) counts[i] = 0;
+        if (n == 0) return;
+        DevBuf<unsigned long long> hist(256, st_);
+        hist.zero();
+        unsigned hgrid = (unsigned)std::min<uint64_t>(div_up(n, 256 * 8), 148 * 16);
+        CBL_LAUNCH((route_hist_kernel<W>), hgrid, 256, 0, st_, (const W*)d_words, n, dg, hist.get());
+        unsigned long long h[ROUTE_MAX_SPLIT + 1];
+        CUDA_CHECK(cudaMemcpyAsync(h, hist.get(), sizeof(h), cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        for (uint32_t i = 0; i <= n_split; i++) counts[i] = h[i];
+    }
+    // every word goes straight to peer_recv[dest][recv_offset[dest] + (rank among this rank's words for dest)];
+    // counts = this rank's per-destination counts (from route_counts_dev); d_pos[i] = slot of word i in send order
+    void route_scatter_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* const* peer_recv,
+                           const uint64_t* recv_offset, const uint64_t* counts, uint32_t* d_pos) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        const DestDigit<W> dg = make_dest_digit(splitters, n_split);
+        if (n == 0) return;
+        if (n > RS_MAX_KEYS) throw Error(CBL_EINVAL, "route batch too large (max 2^30 - 1 words per call)");
+        unsigned long long h_base[512];
+        PeerOuts po;
+        unsigned long long run = 0;
+        for (int d = 0; d < 256; d++) {
+            h_base[d] = d <= (int)n_split ? recv_offset[d] : 0;
+            h_base[256 + d] = run;
+            if (d <= (int)n_split) run += counts[d];
+        }
+        for (int d = 0; d <= ROUTE_MAX_SPLIT; d++) po.p[d] = d <= (int)n_split ? peer_recv[d] : nullptr;
+        if (run != n) throw Error(CBL_EINVAL, "route_scatter: counts do not add up to n");
+        DevBuf<unsigned long long> base(512, st_);
+        CUDA_CHECK(cudaMemcpyAsync(base.get(), h_base, sizeof h_base, cudaMemcpyHostToDevice, st_));
+        const uint64_t tiles = div_up(n, RsTile<W>::TILE);
+        DevBuf<uint32_t> status(tiles * 256, st_), counter(1, st_);
+        status.zero();
+        counter.zero();
+        CBL_LAUNCH((radix_pass_kernel<W, false, DestDigit<W>, true>), (unsigned)tiles, RS_THREADS, sizeof(W) * RsTile<W>::TILE, st_,
+                   (const W*)d_words, (W*)nullptr, nullptr, nullptr, n, dg, base.get(), status.get(), counter.get(), d_pos, po, base.get() + 256);
+        CUDA_CHECK(cudaStreamSynchronize(st_));  // h_base is a stack array; the stores to the peers are complete
+    }
+    void probe_words_scatter_dev(const void* d_words, uint64_t n, uint32_t n_src, const uint64_t* src_begin, uint8_t* const* peer_back,
+                                 const uint64_t* back_offset) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        if (n_src < 1 || n_src > 16) throw Error(CBL_EINVAL, "probe_words_scatter: 1..16 source ranks");
+        if (n == 0) return;
+        PeerBack pb;
+        pb.n_src = (int)n_src;
+        for (uint32_t s = 0; s < 16; s++) {
+            pb.p[s] = s < n_src ? peer_back[s] : nullptr;
+            pb.back_off[s] = s < n_src ? back_offset[s] : 0;
+        }
+        for (uint32_t s = 0; s <= 16; s++) pb.src_begin[s] = s <= n_src ? src_begin[s] : n;
+        if (src_begin[0] != 0 || src_begin[n_src] != n) throw Error(CBL_EINVAL, "probe_words_scatter: src_begin must run from 0 to n");
+        ensure_sub();
+        CBL_LAUNCH((probe_words_scatter_kernel<W, Suf>), (unsigned)div_up(n, 256), 256, 0, st_, (const W*)d_words, n, view(), P_, pb);
+        CUDA_CHECK(cudaStreamSynchronize(st_));
     }
     void gather_u8_dev(const uint8_t* d_src, const uint32_t* d_pos, uint64_t n, uint8_t* d_out) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));

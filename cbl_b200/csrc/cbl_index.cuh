@@ -50,6 +50,12 @@ public:
     virtual void route_words_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* d_send,
                                  uint32_t* d_pos, uint64_t* counts) = 0;
     virtual void gather_u8_dev(const uint8_t* d_src, const uint32_t* d_pos, uint64_t n, uint8_t* d_out) = 0;
+    // fused route + exchange over peer memory (see include/cbl_gpu.h)
+    virtual void route_counts_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, uint64_t* counts) = 0;
+    virtual void route_scatter_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* const* peer_recv,
+                                   const uint64_t* recv_offset, const uint64_t* counts, uint32_t* d_pos) = 0;
+    virtual void probe_words_scatter_dev(const void* d_words, uint64_t n, uint32_t n_src, const uint64_t* src_begin,
+                                         uint8_t* const* peer_back, const uint64_t* back_offset) = 0;
     // set operations
     virtual IIndex* setop(int op, IIndex* other) = 0;
     virtual void setop_assign(int op, IIndex* other) = 0;

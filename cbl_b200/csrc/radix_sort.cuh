@@ -44,6 +44,12 @@ template <class W> struct DestDigit {
     }
 };
 
+// routing straight into the owners' receive buffers: one output base pointer per destination (peer
+// memory mapped with CUDA IPC; the stores travel over NVLink), see cbl_route_scatter_dev
+struct PeerOuts {
+    void* p[ROUTE_MAX_SPLIT + 1];
+};
+
 // All digit histograms in one read of the keys.  hist[pass][256] (u64, zeroed by the caller).
 // Per-warp shared-memory histograms (plain shared atomics: counting needs no order), several keys per
 // thread in flight; one global atomic per (block, pass, digit) at the end.
@@ -108,12 +114,16 @@ __global__ void __launch_bounds__(256) radix_scan_hist_kernel(unsigned long long
 // every peer group adds the group size to its warp's digit counter (shared atomic, returns the base)
 // and broadcasts it; the atomics of one warp execute in program order, which keeps items ordered.
 // Tile prefixes: decoupled look-back, one thread per digit.
-template <class W, bool HAS_VAL, class DigitFn>
+//
+// MULTI_OUT (router only): digit d's keys go to peers.p[d][digit_base[d] + ...] instead of out[...], and
+// pos_out receives local_base[d] + rank of the key among this rank's keys for d (its slot in send order).
+template <class W, bool HAS_VAL, class DigitFn, bool MULTI_OUT = false>
 __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kernel(const W* __restrict__ in, W* __restrict__ out,
                                                                    const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                                    uint64_t n, DigitFn digit, const unsigned long long* __restrict__ digit_base,
                                                                    volatile uint32_t* status, uint32_t* tile_counter,
-                                                                   uint32_t* __restrict__ pos_out) {
+                                                                   uint32_t* __restrict__ pos_out, PeerOuts peers = PeerOuts(),
+                                                                   const unsigned long long* __restrict__ local_base = nullptr) {
     constexpr int ITEMS = RsTile<W>::ITEMS;
     constexpr int TILE = RsTile<W>::TILE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -121,9 +131,12 @@ __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kern
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + sizeof(W) * TILE);  // only if HAS_VAL
     __shared__ uint32_t s_whist[RS_WARPS][256];
     __shared__ long long s_goff[256];
+    __shared__ long long s_loff[MULTI_OUT ? ROUTE_MAX_SPLIT + 1 : 1];
+    __shared__ W* s_outp[MULTI_OUT ? ROUTE_MAX_SPLIT + 1 : 1];
     __shared__ uint32_t s_tmp[33];
     __shared__ uint32_t s_tile;
 
+    if (MULTI_OUT && threadIdx.x <= ROUTE_MAX_SPLIT) s_outp[threadIdx.x] = reinterpret_cast<W*>(peers.p[threadIdx.x]);
     const uint32_t tile = block_ticket(tile_counter, &s_tile);
     const uint64_t tile_base = (uint64_t)tile * TILE;
     const int tile_n = (int)min((uint64_t)TILE, n - tile_base);
@@ -211,6 +224,7 @@ __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kern
             status[(size_t)tile * 256 + t] = RS_FLAG_INCL | (excl + run);
         }
         s_goff[t] = (long long)digit_base[t] + (long long)excl - (long long)dstart;
+        if (MULTI_OUT && t <= ROUTE_MAX_SPLIT) s_loff[t] = (long long)local_base[t] + (long long)excl - (long long)dstart;
     }
     __syncthreads();
 
@@ -223,7 +237,8 @@ __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kern
             const uint32_t pos = s_whist[warp][d] + info[i];
             s_keys[pos] = key[i];
             if (HAS_VAL) s_vals[pos] = val[i];
-            if (DigitFn::WANTS_POS && pos_out != nullptr) pos_out[tile_base + local] = (uint32_t)(s_goff[d] + (long long)pos);
+            if (DigitFn::WANTS_POS && pos_out != nullptr)
+                pos_out[tile_base + local] = (uint32_t)((MULTI_OUT ? s_loff[d] : s_goff[d]) + (long long)pos);
         }
     }
     __syncthreads();
@@ -236,7 +251,8 @@ __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kern
             const W k = s_keys[idx];
             const uint32_t d = digit(k);
             const long long g = s_goff[d] + idx;
-            out[g] = k;
+            if (MULTI_OUT) s_outp[d][g] = k;
+            else out[g] = k;
             if (HAS_VAL) vout[g] = s_vals[idx];
         }
     }

@@ -142,6 +142,72 @@ class GpuEngine:
         return self.seq_words(seq.data_ptr(), np.array([0, n_bases], dtype=np.uint64))
 
 
+class PeerExchange:
+    """Receive / answer buffers of one rank, mapped into every other rank of the box with CUDA IPC, so that
+    the router kernel stores each word directly into its owner's memory over NVLink and the owner's probe
+    kernel stores each answer directly back (no send buffer, no NCCL data path).  The process group only
+    carries the g x g count matrix, the IPC handles and barriers, so it may be NCCL or gloo."""
+
+    def __init__(self, cbl, group, rank: int, world: int, device):
+        self.cbl, self.group, self.rank, self.world, self.device = cbl, group, rank, world, device
+        self.word_bytes = cbl.word_bytes()
+        backend = dist.get_backend(group)
+        self.ctrl = torch.device("cpu") if backend == "gloo" else device
+        self.cap_recv = 0   # words
+        self.cap_back = 0   # bytes
+        self.own_recv = self.own_back = 0
+        self.peer_recv: List[int] = []
+        self.peer_back: List[int] = []
+
+    def barrier(self):
+        if self.ctrl.type == "cpu":
+            dist.barrier(group=self.group)
+        else:
+            dist.barrier(group=self.group, device_ids=[self.device.index])
+
+    def all_counts(self, counts: np.ndarray) -> np.ndarray:
+        """g x g matrix C[s][d] = words rank s sends to rank d."""
+        mine = torch.from_numpy(counts.astype(np.int64)).to(self.ctrl)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine, group=self.group)
+        return torch.stack(out).cpu().numpy().astype(np.uint64)
+
+    def _release(self):
+        for r, p in enumerate(self.peer_recv):
+            if r != self.rank and p:
+                self.cbl.peer_close(p)
+        for r, p in enumerate(self.peer_back):
+            if r != self.rank and p:
+                self.cbl.peer_close(p)
+        self.peer_recv, self.peer_back = [], []
+        self.barrier()  # nobody maps our blocks any more
+        if self.own_recv:
+            self.cbl.peer_free(self.own_recv)
+        if self.own_back:
+            self.cbl.peer_free(self.own_back)
+        self.own_recv = self.own_back = 0
+
+    def ensure(self, need_recv_words: int, need_back_bytes: int):
+        """Collective: every rank calls it with the same arguments (they come from the count matrix)."""
+        if need_recv_words <= self.cap_recv and need_back_bytes <= self.cap_back and self.peer_recv:
+            return
+        self._release()
+        self.cap_recv = max(int(need_recv_words * 1.25) + 1024, self.cap_recv)
+        self.cap_back = max(int(need_back_bytes * 1.25) + 1024, self.cap_back)
+        self.own_recv, h_recv = self.cbl.peer_alloc(self.cap_recv * self.word_bytes)
+        self.own_back, h_back = self.cbl.peer_alloc(self.cap_back)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (h_recv, h_back), group=self.group)
+        self.peer_recv = [self.own_recv if r == self.rank else self.cbl.peer_open(handles[r][0]) for r in range(self.world)]
+        self.peer_back = [self.own_back if r == self.rank else self.cbl.peer_open(handles[r][1]) for r in range(self.world)]
+        self.barrier()
+
+    def close(self):
+        if self.peer_recv or self.own_recv:
+            self._release()
+        self.cap_recv = self.cap_back = 0
+
+
 class ShardedCBL:
     """One CBL set sharded by prefix range over the ranks of ``group`` (default: the world)."""
 
@@ -164,9 +230,20 @@ class ShardedCBL:
                 if self.rank == 0:
                     w = self.engine.sample_words(sample_bases, seed=20240229)
                     sp.copy_(equal_mass_splitters(word_prefixes(w, self.suffix_bits, prefix_bits), self.world))
-                dist.broadcast(sp, src=0, group=group)
+                ctrl = sp.cpu() if dist.get_backend(group) == "gloo" else sp   # gloo: control traffic on CPU tensors
+                dist.broadcast(ctrl, src=0, group=group)
+                sp = ctrl.to(self.device)
         assert sp.numel() == self.world - 1
         self.splitters = sp
+        self.splitters_u32 = sp.cpu().numpy().astype(np.uint32)
+        # data path of the exchange: "peer" = fused route + NVLink stores into the owner's buffers (default on
+        # GPUs), "nccl" = partition into a send buffer + all_to_all_single (also what CPU stand-ins use)
+        import os
+
+        mode = os.environ.get("CBL_EXCHANGE", "peer")
+        self.peer = None
+        if self.world > 1 and mode == "peer" and isinstance(self.engine, GpuEngine):
+            self.peer = PeerExchange(self.engine.cbl, group, self.rank, self.world, self.device)
 
     # -- routing ---------------------------------------------------------------------------------
     def _route_words(self, words: torch.Tensor):
@@ -186,8 +263,32 @@ class ShardedCBL:
         recv, recv_counts = exchange(send, counts, self.group)
         return recv, pos, counts, recv_counts
 
+    def _peer_route(self, words: torch.Tensor, want_pos: bool):
+        """Fused route + exchange.  -> (count matrix C, pos tensor or None); this rank's received words are in
+        self.peer.own_recv, grouped by source rank."""
+        px, cbl = self.peer, self.engine.cbl
+        n = words.shape[0]
+        torch.cuda.current_stream(self.device).synchronize()
+        counts = cbl.route_counts_dev(words.data_ptr(), n, self.splitters_u32)
+        C = px.all_counts(counts)                                   # C[s][d]
+        px.ensure(int(C.sum(axis=0).max()), int(C.sum(axis=1).max()))  # ends with a barrier only when it reallocates
+        px.barrier()                                                # every owner is done with the previous batch
+        recv_offset = C[: self.rank, :].sum(axis=0)                 # my region inside each owner's buffer
+        pos = torch.empty(n, dtype=torch.int32, device=self.device) if want_pos else None
+        cbl.route_scatter_dev(words.data_ptr(), n, self.splitters_u32, px.peer_recv, recv_offset, counts,
+                              pos.data_ptr() if want_pos else 0)
+        px.barrier()                                                # all words have landed
+        return C, pos
+
     def _mutate(self, op: int, d_buf: int, offsets: np.ndarray) -> None:
         words = self.engine.seq_words(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
+        if self.peer is not None:
+            C, _ = self._peer_route(words, want_pos=False)
+            del words
+            n_recv = int(C[:, self.rank].sum())
+            if n_recv:
+                self.engine.cbl.words_op_dev(op, self.peer.own_recv, n_recv, 0)
+            return
         recv, _, _, _ = self._route_words(words)
         self.engine.words_op(op, recv, want_flags=False)
 
@@ -199,6 +300,19 @@ class ShardedCBL:
         self._mutate(2, d_buf, offsets)
 
     def contains_words(self, words: torch.Tensor) -> torch.Tensor:
+        if self.peer is not None:
+            px, cbl = self.peer, self.engine.cbl
+            n = words.shape[0]
+            C, pos = self._peer_route(words, want_pos=True)
+            col = C[:, self.rank]
+            src_begin = np.concatenate([[0], np.cumsum(col)]).astype(np.uint64)
+            back_offset = C[:, : self.rank].sum(axis=1)             # where my answers start inside each source's buffer
+            cbl.probe_words_scatter_dev(px.own_recv, int(col.sum()), src_begin, px.peer_back, back_offset)
+            px.barrier()                                            # all answers have landed
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+            if n:
+                cbl.gather_u8_dev(px.own_back, pos.data_ptr(), n, out.data_ptr())
+            return out
         recv, pos, counts, recv_counts = self._route_words(words)
         flags = self.engine.words_op(0, recv, want_flags=True)
         if self.world > 1:
@@ -237,18 +351,25 @@ class ShardedCBL:
     def local_count(self) -> int:
         return self.engine.count()
 
-    def count(self) -> int:
-        c = torch.tensor([self.engine.count()], dtype=torch.int64, device=self.device)
-        if self.world > 1:
-            dist.all_reduce(c, group=self.group)
+    def _sum_over_ranks(self, v: int) -> int:
+        if self.world == 1:
+            return int(v)
+        dev = torch.device("cpu") if dist.get_backend(self.group) == "gloo" else self.device
+        c = torch.tensor([int(v)], dtype=torch.int64, device=dev)
+        dist.all_reduce(c, group=self.group)
         return int(c.item())
+
+    def count(self) -> int:
+        return self._sum_over_ranks(self.engine.count())
 
     def num_buckets(self) -> int:
         nb = getattr(self.engine, "cbl", None)
-        c = torch.tensor([nb.num_buckets() if nb is not None else 0], dtype=torch.int64, device=self.device)
-        if self.world > 1:
-            dist.all_reduce(c, group=self.group)
-        return int(c.item())
+        return self._sum_over_ranks(nb.num_buckets() if nb is not None else 0)
+
+    def close(self) -> None:
+        """Collective: unmap / free the peer buffers."""
+        if self.peer is not None:
+            self.peer.close()
 
     def stream_ptr(self) -> int:
         return self.engine.cbl.stream_ptr()

@@ -114,6 +114,26 @@ int32_t cbl_route_words_dev(cbl_t* h, const void* d_words, size_t n, const uint3
                             uint32_t* d_pos, uint64_t* counts);
 /* d_out[i] = d_src[d_pos[i]] — puts the answers that came back from the owners into read order */
 int32_t cbl_gather_u8_dev(cbl_t* h, const uint8_t* d_src, const uint32_t* d_pos, size_t n, uint8_t* d_out);
+/* ---- fused route + exchange over NVLink peer memory (one process per GPU, buffers shared with CUDA IPC).
+ *      Replaces "partition into a send buffer, then NCCL all-to-all" by ONE kernel whose coalesced stores
+ *      land directly in the owner's receive buffer; NCCL (or gloo) only carries the count matrix and barriers. */
+#define CBL_IPC_HANDLE_BYTES 64
+/* a cudaMalloc block other processes may map: handle receives the CUDA IPC handle (CBL_IPC_HANDLE_BYTES bytes) */
+int32_t cbl_peer_alloc(cbl_t* h, size_t bytes, void** d_ptr, uint8_t* handle);
+int32_t cbl_peer_open(cbl_t* h, const uint8_t* handle, void** d_ptr);   /* map a peer's block (lazy peer access) */
+int32_t cbl_peer_close(cbl_t* h, void* d_ptr);                          /* unmap */
+int32_t cbl_peer_free(cbl_t* h, void* d_ptr);                           /* free an own block (peers must have unmapped it) */
+/* words per owner rank (host array of n_splitters + 1 counts) */
+int32_t cbl_route_counts_dev(cbl_t* h, const void* d_words, size_t n, const uint32_t* splitters, uint32_t n_splitters, uint64_t* counts);
+/* word i goes to peer_recv[d][recv_offset[d] + j], d = its owner, j = its rank among this rank's words for d
+ * (stable); counts = this rank's cbl_route_counts_dev result; d_pos[i] (may be NULL) = slot of word i in
+ * destination-major send order (what cbl_gather_u8_dev needs).  Returns when the stores are complete. */
+int32_t cbl_route_scatter_dev(cbl_t* h, const void* d_words, size_t n, const uint32_t* splitters, uint32_t n_splitters,
+                              void* const* peer_recv, const uint64_t* recv_offset, const uint64_t* counts, uint32_t* d_pos);
+/* membership of n received words; words [src_begin[s], src_begin[s+1]) came from rank s and answer j of that
+ * range is stored to peer_back[s][back_offset[s] + j].  n_src <= 16.  Returns when the stores are complete. */
+int32_t cbl_probe_words_scatter_dev(cbl_t* h, const void* d_words, size_t n, uint32_t n_src, const uint64_t* src_begin,
+                                    uint8_t* const* peer_back, const uint64_t* back_offset);
 int32_t cbl_word_bytes(const cbl_t* h, int32_t* out);      /* 8 or 16: size of one device word */
 int32_t cbl_suffix_bits(const cbl_t* h, int32_t* out);
 
