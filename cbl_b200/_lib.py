@@ -56,6 +56,7 @@ SIGNATURES = {
     "cbl_load_from_file": (C.c_int32, [vp, C.c_char_p, vpp]),
     "cbl_seq_words_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t, vp]),
     "cbl_words_op_dev": (C.c_int32, [vp, C.c_int32, vp, C.c_size_t, vp]),
+    "cbl_words_op_segments_dev": (C.c_int32, [vp, C.c_int32, vpp, u64p, C.c_uint32]),
     "cbl_export_words_dev": (C.c_int32, [vp, C.c_uint64, C.c_uint64, vp]),
     "cbl_route_words_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, vp, vp, u64p]),
     "cbl_gather_u8_dev": (C.c_int32, [vp, vp, vp, C.c_size_t, vp]),
@@ -65,7 +66,7 @@ SIGNATURES = {
     "cbl_peer_free": (C.c_int32, [vp, vp]),
     "cbl_route_counts_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, u64p]),
     "cbl_route_scatter_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, vpp, u64p, u64p, vp]),
-    "cbl_probe_words_scatter_dev": (C.c_int32, [vp, vp, C.c_size_t, C.c_uint32, u64p, vpp, u64p]),
+    "cbl_seq_route_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t, u32p, C.c_uint32, vpp, C.c_uint64, vp, u64p]),
     "cbl_word_bytes": (C.c_int32, [vp, i32p]),
     "cbl_suffix_bits": (C.c_int32, [vp, i32p]),
     "cbl_seq_words": (C.c_int32, [vp, vp, u64p, C.c_size_t, u64p, u64p, C.c_int32]),

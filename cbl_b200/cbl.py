@@ -241,12 +241,23 @@ class CBL:
         self._chk(self._L.cbl_route_scatter_dev(self._h, d_words, n, sp.ctypes.data_as(u32p), len(sp), C.cast(ptrs, vpp_t), ro.ctypes.data_as(u64p),
                                                 ct.ctypes.data_as(u64p), d_pos))
 
-    def probe_words_scatter_dev(self, d_words: int, n: int, src_begin, peer_back, back_offset) -> None:
-        sb = np.ascontiguousarray(src_begin, dtype=np.uint64)
-        g = len(sb) - 1
-        ptrs = (C.c_void_p * g)(*[int(x) for x in peer_back])
-        bo = np.ascontiguousarray(back_offset, dtype=np.uint64)
-        self._chk(self._L.cbl_probe_words_scatter_dev(self._h, d_words, n, g, sb.ctypes.data_as(u64p), C.cast(ptrs, vpp_t), bo.ctypes.data_as(u64p)))
+    def seq_route_dev(self, d_buf: int, offsets: np.ndarray, splitters: np.ndarray, peer_region, cap: int, d_pos: int = 0) -> np.ndarray:
+        """Fused encode + necklace + route: the words of the records go straight into ``peer_region[d]`` (this rank's
+        region, ``cap`` words, inside owner d's receive buffer).  Returns the per-owner counts (> cap = overflow)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        sp = np.ascontiguousarray(splitters, dtype=np.uint32)
+        g = len(sp) + 1
+        ptrs = (C.c_void_p * g)(*[int(x) for x in peer_region])
+        counts = np.zeros(g, dtype=np.uint64)
+        self._chk(self._L.cbl_seq_route_dev(self._h, d_buf, offsets.ctypes.data_as(u64p), len(offsets) - 1, sp.ctypes.data_as(u32p), len(sp),
+                                            C.cast(ptrs, vpp_t), cap, d_pos, counts.ctypes.data_as(u64p)))
+        return counts
+
+    def words_op_segments_dev(self, op: int, seg_ptrs, seg_n) -> None:
+        g = len(seg_ptrs)
+        ptrs = (C.c_void_p * g)(*[int(x) for x in seg_ptrs])
+        n = np.ascontiguousarray(seg_n, dtype=np.uint64)
+        self._chk(self._L.cbl_words_op_segments_dev(self._h, op, C.cast(ptrs, vpp_t), n.ctypes.data_as(u64p), g))
 
     def gather_u8_dev(self, d_src: int, d_pos: int, n: int, d_out: int) -> None:
         self._chk(self._L.cbl_gather_u8_dev(self._h, d_src, d_pos, n, d_out))

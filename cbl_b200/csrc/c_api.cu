@@ -381,6 +381,15 @@ int32_t cbl_words_op_dev(cbl_t* h, int32_t op, const void* d_words, size_t n, ui
         h->ix->sync();
     });
 }
+int32_t cbl_words_op_segments_dev(cbl_t* h, int32_t op, const void* const* seg, const uint64_t* seg_n, uint32_t n_seg) {
+    return guard(h, [&] {
+        need(h, "handle");
+        if (n_seg) { need(seg, "seg"); need(seg_n, "seg_n"); }
+        if (op < 1 || op > 2) throw Error(CBL_EINVAL, "words_op_segments: op must be 1 (insert) or 2 (remove)");
+        h->ix->words_op_segments_dev(op, seg, seg_n, n_seg);
+        h->ix->sync();
+    });
+}
 int32_t cbl_export_words_dev(cbl_t* h, uint64_t start, uint64_t count, void* d_out) {
     return guard(h, [&] { need(h, "handle"); if (count) need(d_out, "d_out"); h->ix->export_words_dev(start, count, 0, d_out); h->ix->sync(); });
 }
@@ -417,12 +426,12 @@ int32_t cbl_route_scatter_dev(cbl_t* h, const void* d_words, size_t n, const uin
         h->ix->route_scatter_dev(d_words, n, splitters, n_splitters, peer_recv, recv_offset, counts, d_pos);
     });
 }
-int32_t cbl_probe_words_scatter_dev(cbl_t* h, const void* d_words, size_t n, uint32_t n_src, const uint64_t* src_begin,
-                                    uint8_t* const* peer_back, const uint64_t* back_offset) {
+int32_t cbl_seq_route_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, const uint32_t* splitters,
+                          uint32_t n_splitters, void* const* peer_region, uint64_t cap, uint32_t* d_pos, uint64_t* counts) {
     return guard(h, [&] {
-        need(h, "handle"); need(src_begin, "src_begin"); need(peer_back, "peer_back"); need(back_offset, "back_offset");
-        if (n) need(d_words, "d_words");
-        h->ix->probe_words_scatter_dev(d_words, n, n_src, src_begin, peer_back, back_offset);
+        need(h, "handle"); need(d_buf, "d_buf"); need(offsets, "offsets"); need(peer_region, "peer_region"); need(counts, "counts");
+        if (n_splitters) need(splitters, "splitters");
+        h->ix->seq_route_dev(d_buf, offsets[n_seqs], offsets, n_seqs, splitters, n_splitters, peer_region, cap, d_pos, counts);
     });
 }
 // ---- peer memory: plain cudaMalloc blocks shared between the processes of one box with CUDA IPC ----

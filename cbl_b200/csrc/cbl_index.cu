@@ -279,12 +279,24 @@ public:
         if (b.n_chunks == 0) return;
         unsigned grid = (unsigned)std::min<uint64_t>(b.n_chunks, 1u << 30);
         IndexView<Suf> v = view();
+        const ShardArgs<W> sa{};
         if (mode == 0) {
-            if (brute) CBL_LAUNCH((seq_words_kernel<W, Suf, 0, true, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
-            else CBL_LAUNCH((seq_words_kernel<W, Suf, 0, false, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
+            if (brute) CBL_LAUNCH((seq_words_kernel<W, Suf, 0, true, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
+            else CBL_LAUNCH((seq_words_kernel<W, Suf, 0, false, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
         } else {
-            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err);
+            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
         }
+    }
+    // membership of n words (MODE 3 of the fused kernel: same staged probe + deferred queue, no sequence front end);
+    // d_flags may be peer memory
+    void launch_probe_words(const W* d_words, uint64_t n, uint8_t* d_flags, cudaStream_t s) {
+        if (n == 0) return;
+        ShardArgs<W> sa{};
+        sa.in_words = d_words;
+        sa.n_in = n;
+        const unsigned grid = (unsigned)std::min<uint64_t>(div_up(n, CHUNK_KMERS), 1u << 30);
+        CBL_LAUNCH((seq_words_kernel<W, Suf, 3, false, 32, 1>), grid, SW_THREADS, 0, s, SeqBatch{}, P_, (W*)nullptr, d_flags, view(),
+                   (unsigned long long*)nullptr, sa);
     }
     static void throw_bad_byte(unsigned long long e) {
         throw Error(CBL_EINVAL, "non-ACGT byte in sequence near byte offset " + std::to_string(e) +
@@ -771,7 +783,7 @@ public:
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         if (n == 0) return;
         if (d_out) ensure_sub();
-        if (d_out) CBL_LAUNCH((probe_words_kernel<W, Suf>), (unsigned)div_up(n, 256), 256, 0, st_, (const W*)d_words, n, view(), P_, d_out);
+        if (d_out) launch_probe_words((const W*)d_words, n, d_out, st_);
         if (op == 0) return;
         uint64_t done = 0;
         while (done < n) {
@@ -780,6 +792,29 @@ public:
             CUDA_CHECK(cudaMemcpyAsync(a.get(), (const W*)d_words + done, m * sizeof(W), cudaMemcpyDeviceToDevice, st_));
             mutate_with_words(a.get(), b.get(), m, op == 1 ? EDIT_INS : EDIT_DEL);
             done += m;
+        }
+    }
+    // insert / remove the words of several device segments (the per-source regions of a sharded receive buffer) as ONE
+    // batch: the segments are gathered into the sort buffer, so the shard is rewritten once, not once per segment
+    void words_op_segments_dev(int op, const void* const* seg, const uint64_t* seg_n, uint32_t n_seg) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        uint64_t remaining = 0;
+        for (uint32_t i = 0; i < n_seg; i++) remaining += seg_n[i];
+        uint32_t si = 0;
+        uint64_t so = 0;
+        while (remaining) {
+            const uint64_t m = std::min<uint64_t>(batch_kmers_, remaining);
+            DevBuf<W> a(m, st_), b(m, st_);
+            uint64_t filled = 0;
+            while (filled < m) {
+                const uint64_t take = std::min<uint64_t>(seg_n[si] - so, m - filled);
+                if (take) CUDA_CHECK(cudaMemcpyAsync(a.get() + filled, (const W*)seg[si] + so, take * sizeof(W), cudaMemcpyDeviceToDevice, st_));
+                filled += take;
+                so += take;
+                if (so == seg_n[si]) { si++; so = 0; }
+            }
+            mutate_with_words(a.get(), b.get(), m, op == 1 ? EDIT_INS : EDIT_DEL);
+            remaining -= m;
         }
     }
     void kmers_op(int op, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out) override {
@@ -883,22 +918,37 @@ public:
                    (const W*)d_words, (W*)nullptr, nullptr, nullptr, n, dg, base.get(), status.get(), counter.get(), d_pos, po, base.get() + 256);
         CUDA_CHECK(cudaStreamSynchronize(st_));  // h_base is a stack array; the stores to the peers are complete
     }
-    void probe_words_scatter_dev(const void* d_words, uint64_t n, uint32_t n_src, const uint64_t* src_begin, uint8_t* const* peer_back,
-                                 const uint64_t* back_offset) override {
+    // Fused encode + necklace + route (seq_words_kernel MODE 2): every word of the records goes straight into this rank's
+    // region (cap words) of its owner's receive buffer; counts[d] = words reserved for owner d (> cap: nothing of the
+    // overflow was written, the caller retries with a larger cap); d_pos[i] = d * cap + index inside the region.
+    void seq_route_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, const uint32_t* splitters,
+                       uint32_t n_split, void* const* peer_region, uint64_t cap, uint32_t* d_pos, uint64_t* counts) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
-        if (n_src < 1 || n_src > 16) throw Error(CBL_EINVAL, "probe_words_scatter: 1..16 source ranks");
-        if (n == 0) return;
-        PeerBack pb;
-        pb.n_src = (int)n_src;
-        for (uint32_t s = 0; s < 16; s++) {
-            pb.p[s] = s < n_src ? peer_back[s] : nullptr;
-            pb.back_off[s] = s < n_src ? back_offset[s] : 0;
-        }
-        for (uint32_t s = 0; s <= 16; s++) pb.src_begin[s] = s <= n_src ? src_begin[s] : n;
-        if (src_begin[0] != 0 || src_begin[n_src] != n) throw Error(CBL_EINVAL, "probe_words_scatter: src_begin must run from 0 to n");
-        ensure_sub();
-        CBL_LAUNCH((probe_words_scatter_kernel<W, Suf>), (unsigned)div_up(n, 256), 256, 0, st_, (const W*)d_words, n, view(), P_, pb);
-        CUDA_CHECK(cudaStreamSynchronize(st_));
+        check_records(offsets, n_seqs);
+        ShardArgs<W> sa{};
+        sa.dest = make_dest_digit(splitters, n_split);
+        for (uint32_t i = 0; i <= ROUTE_MAX_SPLIT; i++) sa.peer[i] = i <= n_split ? (W*)peer_region[i] : nullptr;
+        for (uint32_t i = 0; i <= n_split; i++) counts[i] = 0;
+        if ((uint64_t)(n_split + 1) * cap >= (1ull << 32)) throw Error(CBL_EINVAL, "seq_route: (ranks x region capacity) must stay below 2^32 words");
+        PieceList pl;
+        build_pieces(offsets, 0, n_seqs, pl);
+        if (pl.kmers.empty()) return;
+        DevPieces dp;
+        upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, st_);
+        DevBuf<unsigned long long> cnt(17, st_);   // [16] per-owner counters, [16] = error offset
+        CUDA_CHECK(cudaMemsetAsync(cnt.get(), 0, 16 * 8, st_));
+        CUDA_CHECK(cudaMemsetAsync(cnt.get() + 16, 0xFF, 8, st_));
+        sa.cnt = cnt.get();
+        sa.pos = d_pos;
+        sa.cap = cap;
+        const unsigned grid = (unsigned)std::min<uint64_t>(dp.batch.n_chunks, 1u << 30);
+        CBL_LAUNCH((seq_words_kernel<W, Suf, 2, false, 32, 1>), grid, SW_THREADS, 0, st_, dp.batch, P_, (W*)nullptr, (uint8_t*)nullptr, view(),
+                   cnt.get() + 16, sa);
+        unsigned long long h[17];
+        CUDA_CHECK(cudaMemcpyAsync(h, cnt.get(), sizeof h, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));   // the stores to the peers are complete
+        if (h[16] != ULLONG_MAX) throw_bad_byte(h[16]);
+        for (uint32_t i = 0; i <= n_split; i++) counts[i] = h[i];
     }
     void gather_u8_dev(const uint8_t* d_src, const uint32_t* d_pos, uint64_t n, uint8_t* d_out) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));

@@ -46,6 +46,7 @@ public:
     virtual void kmers_op(int op /*0 contains,1 insert,2 remove*/, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out) = 0;
     // words (already transformed) — used by the sharded multi-GPU path after the all-to-all
     virtual void words_op_dev(int op, const void* d_words, uint64_t n, uint8_t* d_out) = 0;
+    virtual void words_op_segments_dev(int op, const void* const* seg, const uint64_t* seg_n, uint32_t n_seg) = 0;
     // multi-GPU routing: stable partition of words by owner rank (dest = #splitters <= prefix)
     virtual void route_words_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* d_send,
                                  uint32_t* d_pos, uint64_t* counts) = 0;
@@ -54,8 +55,8 @@ public:
     virtual void route_counts_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, uint64_t* counts) = 0;
     virtual void route_scatter_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* const* peer_recv,
                                    const uint64_t* recv_offset, const uint64_t* counts, uint32_t* d_pos) = 0;
-    virtual void probe_words_scatter_dev(const void* d_words, uint64_t n, uint32_t n_src, const uint64_t* src_begin,
-                                         uint8_t* const* peer_back, const uint64_t* back_offset) = 0;
+    virtual void seq_route_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, const uint32_t* splitters,
+                               uint32_t n_split, void* const* peer_region, uint64_t cap, uint32_t* d_pos, uint64_t* counts) = 0;
     // set operations
     virtual IIndex* setop(int op, IIndex* other) = 0;
     virtual void setop_assign(int op, IIndex* other) = 0;

@@ -357,27 +357,6 @@ __global__ void probe_words_kernel(const W* __restrict__ words, uint64_t n, Inde
     if (i < n) out[i] = contains_key<W, Suf>(ix, P, words[i]) ? 1 : 0;
 }
 
-// Sharded contains: membership of the words received from the other ranks, every answer stored
-// DIRECTLY into the answer buffer of the rank the word came from (peer memory, NVLink stores).
-// Words [src_begin[s], src_begin[s + 1]) came from rank s; answer j of that range goes to
-// back[s][back_off[s] + j].
-struct PeerBack {
-    uint8_t* p[16];
-    unsigned long long src_begin[17];
-    unsigned long long back_off[16];
-    int n_src;
-};
-template <class W, class Suf>
-__global__ void probe_words_scatter_kernel(const W* __restrict__ words, uint64_t n, IndexView<Suf> ix, KParams P, PeerBack pb) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t f = contains_key<W, Suf>(ix, P, words[i]) ? 1 : 0;
-    int s = 0;
-#pragma unroll
-    for (int t = 1; t < 16; t++) s += (t < pb.n_src) && (i >= pb.src_begin[t]);
-    pb.p[s][pb.back_off[s] + (i - pb.src_begin[s])] = f;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Interpolation corrections for the membership probe (index_view.cuh): one signed byte per group of
 // SUB_GROUP suffixes.  Slot q belongs to the bucket that holds element q * SUB_GROUP; if it is one of

@@ -39,7 +39,7 @@ template <class W> struct DestDigit {
         const uint32_t prefix = (uint32_t)(key >> suffix_bits);
         uint32_t d = 0;
 #pragma unroll
-        for (int i = 0; i < ROUTE_MAX_SPLIT; i++) d += (i < (int)n_split) && (split[i] <= prefix);
+        for (int i = 0; i < ROUTE_MAX_SPLIT; i++) d += split[i] <= prefix;   // unused splitters hold 0xFFFFFFFF > any prefix (PREFIX_BITS <= 31)
         return d;
     }
 };

@@ -11,8 +11,28 @@
 // reverse-complemented ones" order of src/cbl.rs:248-275 with ballot prefix counts.
 #pragma once
 #include "index_view.cuh"
+#include "radix_sort.cuh"   // DestDigit (owner rank of a word)
 
 namespace cbl {
+
+// Arguments of the sharded modes of seq_words_kernel (multi-GPU path, cbl_b200/sharded.py).
+// MODE 2 (source side): every word is stored DIRECTLY into the receive buffer of the rank that owns its prefix
+// (peer memory mapped with CUDA IPC, the stores travel over NVLink).  peer[d] already points at THIS rank's
+// region inside owner d's buffer; a region holds `cap` words.  Space is reserved chunk by chunk with one atomic
+// per (chunk, owner) on the device-local counters cnt[16], so no counting pass and no send buffer exist.
+// pos[i] = d * cap + (index of word i inside the region) tells where the answer of k-mer i will come back.
+// A region that would overflow is not written; cnt[d] > cap afterwards tells the host to retry with a larger cap.
+// MODE 3 (owner side): membership of in_words[0, n_in), one answer byte per word to out_flags, which may itself
+// be peer memory (the answer region inside the source rank's buffer).
+template <class W> struct ShardArgs {
+    const W* in_words = nullptr;          // MODE 3
+    unsigned long long n_in = 0;          // MODE 3
+    DestDigit<W> dest;                    // MODE 2: owner rank of a word
+    W* peer[ROUTE_MAX_SPLIT + 1];         // MODE 2
+    unsigned long long* cnt = nullptr;    // MODE 2: [16] words reserved per owner (zeroed by the caller)
+    uint32_t* pos = nullptr;              // MODE 2: may be null (mutations need no answers)
+    unsigned long long cap = 0;           // MODE 2: words per region
+};
 
 constexpr int CHUNK_KMERS = 2048;  // src/cbl.rs:67 CHUNK_SIZE
 constexpr int SW_THREADS = 64;
@@ -83,6 +103,9 @@ template <> __device__ __forceinline__ u128 cut_window<u128>(uint64_t A, uint64_
 }
 
 // MODE 0: write words (W) to out_words.   MODE 1: probe the index, write one byte per k-mer.
+// MODE 2: fused route (sharded path, source side): the words go straight to their owner ranks, see ShardArgs.
+// MODE 3: the words are read from sa.in_words instead of being computed (sharded path, owner side, and the
+//         word-level contains of the C ABI); answers to out_flags.
 // BRUTE: use the normative brute-force necklace instead of the fast one (debug / cross-check).
 // U: k-mers per lane processed together.  In MODE 1 the U lookups advance in lock step (directory
 // words, bucket ranges, correction bytes, suffix windows), each stage issuing U independent loads.
@@ -92,19 +115,30 @@ template <> __device__ __forceinline__ u128 cut_window<u128>(uint64_t A, uint64_
 #define CBL_SW_MIN_BLOCKS 24   // fused probe: latency bound, occupancy beats a few spilled registers (measured)
 #endif
 template <class W, class Suf, int MODE, bool BRUTE, int WB, int U>
-__global__ void __launch_bounds__(SW_THREADS, (MODE == 1 && U == 1) ? CBL_SW_MIN_BLOCKS : 1) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
+__global__ void __launch_bounds__(SW_THREADS, ((MODE == 1 || MODE == 3) && U == 1) ? CBL_SW_MIN_BLOCKS : 1) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
                                                                uint8_t* __restrict__ out_flags, IndexView<Suf> ix,
-                                                               unsigned long long* __restrict__ err_pos) {
+                                                               unsigned long long* __restrict__ err_pos, ShardArgs<W> sa) {
     static_assert(32 % U == 0, "U must divide 32");
     constexpr int WN = Window<Suf, WB>::N;
-    constexpr int QN = MODE == 1 ? PENDING_CAP : 1;
+    constexpr bool PROBE = MODE == 1 || MODE == 3;
+    constexpr int QN = PROBE ? PENDING_CAP : 1;
+    // MODE 2: the chunk's words (by output slot), owner | rank-inside-owner of every slot, slots in owner order
+    constexpr int RN = MODE == 2 ? CHUNK_KMERS : 1;
+    __shared__ W s_stage[RN];
+    __shared__ uint16_t s_dr[RN], s_inv[RN];
+    __shared__ uint32_t s_cnt[16], s_off[17], s_base[16];
+    __shared__ W* s_peer[16];
+    if (MODE == 2) {
+        if (threadIdx.x < 16) { s_cnt[threadIdx.x] = 0; s_peer[threadIdx.x] = sa.peer[threadIdx.x]; }
+        __syncthreads();
+    }
     __shared__ uint32_t s_fwd[2][32];
     __shared__ uint32_t s_piece;
     // MODE 1: answers of the chunk (written out coalesced at the end) and, per warp, the queue of
     // lookups their first window did not decide.  Those are not finished on the spot (that would
     // stall the other lanes of the warp, 4 of 5 of which are already done) but collected and worked
     // off 32 at a time, one window per lane per round.
-    __shared__ uint8_t s_flags[MODE == 1 ? CHUNK_KMERS : 4];
+    __shared__ __align__(16) uint8_t s_flags[PROBE ? CHUNK_KMERS : 16];
     __shared__ uint4 q_a[2][QN];                 // {L, R, g, span}
     __shared__ PendingKey<Suf> q_b[2][QN];       // {suffix, slot | rounds << 16}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,29 +190,40 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 1 && U == 1) ? CBL_SW_MIN
         }
         q_push(und, s, L, R, g, a.w, slot_it);
     };
-    for (uint64_t chunk = blockIdx.x; chunk < b.n_chunks; chunk += gridDim.x) {
-        if (threadIdx.x == 0) s_piece = (uint32_t)(upper_bound_dev<uint64_t>(b.piece_chunk0, (uint64_t)b.n_pieces + 1, chunk) - 1);
-        __syncthreads();
-        const uint32_t piece = s_piece;
-        const uint64_t ci = chunk - b.piece_chunk0[piece];
-        const uint32_t pk = b.piece_kmers[piece];
-        const uint32_t ks = (uint32_t)(ci * CHUNK_KMERS);
-        const int m = (int)min((uint32_t)CHUNK_KMERS, pk - ks);           // k-mers in this chunk
-        const uint8_t* cbase = b.seq + b.piece_byte[piece] + ks;          // first byte of the chunk
-        const int nbytes = m + P.k - 1;                                   // bytes the chunk may read
-        W* ow = MODE == 0 ? out_words + b.piece_out[piece] + ks : nullptr;
-        uint8_t* of = MODE == 1 ? out_flags + b.piece_out[piece] + ks : nullptr;
+    const uint64_t n_chunks = MODE == 3 ? div_up(sa.n_in, CHUNK_KMERS) : b.n_chunks;
+    for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        int m;
+        W* ow = nullptr;
+        uint8_t* of = nullptr;
+        uint32_t* opos = nullptr;
+        uint64_t Wd = 0, H = 0;
+        if (MODE == 3) {
+            m = (int)min((unsigned long long)CHUNK_KMERS, sa.n_in - chunk * CHUNK_KMERS);
+            of = out_flags + chunk * CHUNK_KMERS;
+        } else {
+            if (threadIdx.x == 0) s_piece = (uint32_t)(upper_bound_dev<uint64_t>(b.piece_chunk0, (uint64_t)b.n_pieces + 1, chunk) - 1);
+            __syncthreads();
+            const uint32_t piece = s_piece;
+            const uint64_t ci = chunk - b.piece_chunk0[piece];
+            const uint32_t pk = b.piece_kmers[piece];
+            const uint32_t ks = (uint32_t)(ci * CHUNK_KMERS);
+            m = (int)min((uint32_t)CHUNK_KMERS, pk - ks);                     // k-mers in this chunk
+            const uint8_t* cbase = b.seq + b.piece_byte[piece] + ks;          // first byte of the chunk
+            const int nbytes = m + P.k - 1;                                   // bytes the chunk may read
+            ow = MODE == 0 ? out_words + b.piece_out[piece] + ks : nullptr;
+            of = MODE == 1 ? out_flags + b.piece_out[piece] + ks : nullptr;
+            opos = (MODE == 2 && sa.pos) ? sa.pos + b.piece_out[piece] + ks : nullptr;
 
-        // pack: lane l holds bases [1024*warp + 32*l, +32); lanes 0,1 also hold the two halo words
-        bool bad = false;
-        const int off = 1024 * warp + 32 * lane;
-        uint64_t Wd = load_pack32(cbase + off, b.seq_end, min(32, nbytes - off), bad);
-        uint64_t H = 0;
-        if (lane < 2) {
-            const int hoff = 1024 * warp + 1024 + 32 * lane;
-            H = load_pack32(cbase + hoff, b.seq_end, min(32, nbytes - hoff), bad);
+            // pack: lane l holds bases [1024*warp + 32*l, +32); lanes 0,1 also hold the two halo words
+            bool bad = false;
+            const int off = 1024 * warp + 32 * lane;
+            Wd = load_pack32(cbase + off, b.seq_end, min(32, nbytes - off), bad);
+            if (lane < 2) {
+                const int hoff = 1024 * warp + 1024 + 32 * lane;
+                H = load_pack32(cbase + hoff, b.seq_end, min(32, nbytes - hoff), bad);
+            }
+            if (bad) atomicMin(err_pos, (unsigned long long)(b.piece_byte[piece] + ks + off));
         }
-        if (bad) atomicMin(err_pos, (unsigned long long)(b.piece_byte[piece] + ks + off));
 
         // Wd1 / Wd2: the packed words one and two lanes further on (wrapping into the halo words held
         // by lanes 0 and 1), so the window loops need plain broadcasts only
@@ -186,7 +231,7 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 1 && U == 1) ? CBL_SW_MIN
         const uint64_t Wd2 = __shfl_sync(0xffffffffu, lane < 2 ? H : Wd, (lane + 2) & 31);
         const int kbase = 1024 * warp;
         uint32_t fwd_before = 0, nfwd_total = 0;
-        if (P.canonical) {
+        if (MODE != 3 && P.canonical) {
             // pass 1: parity of every window -> ballots, so output slots are known up front
             for (int j = 0; j < 32; j++) {
                 uint64_t A = __shfl_sync(0xffffffffu, Wd, j);
@@ -219,6 +264,10 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 1 && U == 1) ? CBL_SW_MIN
                 active[u] = kidx < m;
                 W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
                 slot[u] = (uint32_t)kidx;
+                if (MODE == 3) {
+                    word[u] = active[u] ? sa.in_words[chunk * CHUNK_KMERS + kidx] : (W)0;
+                    continue;
+                }
                 if (P.canonical) {
                     const uint32_t bal = s_fwd[warp][j];
                     const uint32_t fb = fwd_before + __popc(bal & lanemask_lt());
@@ -232,6 +281,15 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 1 && U == 1) ? CBL_SW_MIN
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     if (active[u]) ow[slot[u]] = word[u];
+            } else if (MODE == 2) {
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (active[u]) {
+                        const uint32_t d = sa.dest(word[u]);
+                        const uint32_t r = atomicAdd(&s_cnt[d], 1u);   // rank among the chunk's words for owner d
+                        s_stage[slot[u]] = word[u];
+                        s_dr[slot[u]] = (uint16_t)((d << 11) | r);
+                    }
             } else {
                 // staged membership probe (index_view.cuh): every stage issues U independent loads
                 Suf s[U];
@@ -275,12 +333,51 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 1 && U == 1) ? CBL_SW_MIN
                 }
             }
         }
-        if (MODE == 1) {
+        if (PROBE) {
             while (q_count > 0) q_drain();
             __syncthreads();
-            for (int i = threadIdx.x; i < m; i += SW_THREADS) of[i] = s_flags[i];
+            if (((uintptr_t)of & 15) == 0) {   // 16 answers per store (always the case for MODE 3: NVLink-friendly)
+                const int m16 = m >> 4;
+                for (int i = threadIdx.x; i < m16; i += SW_THREADS) reinterpret_cast<uint4*>(of)[i] = reinterpret_cast<const uint4*>(s_flags)[i];
+                for (int i = (m16 << 4) + threadIdx.x; i < m; i += SW_THREADS) of[i] = s_flags[i];
+            } else {
+                for (int i = threadIdx.x; i < m; i += SW_THREADS) of[i] = s_flags[i];
+            }
         }
-        __syncthreads();  // s_piece / s_fwd reuse in the next grid-stride iteration
+        if (MODE == 2) {
+            __syncthreads();  // s_stage / s_dr / s_cnt of the chunk are complete
+            if (threadIdx.x < 16) {
+                const uint32_t c = s_cnt[threadIdx.x];
+                uint32_t inc = c;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                s_off[threadIdx.x] = inc - c;
+                if (threadIdx.x == 15) s_off[16] = inc;
+                unsigned long long base = 0;
+                if (c) base = atomicAdd(sa.cnt + threadIdx.x, (unsigned long long)c);   // reserve c slots in my region at owner d
+                s_base[threadIdx.x] = (base + c <= sa.cap) ? (uint32_t)base : 0xFFFFFFFFu;
+                s_cnt[threadIdx.x] = 0;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < m; i += SW_THREADS) {
+                const uint32_t dr = s_dr[i], d = dr >> 11, r = dr & 2047u;
+                s_inv[s_off[d] + r] = (uint16_t)i;
+                if (opos) opos[i] = (uint32_t)(d * sa.cap) + s_base[d] + r;
+            }
+            __syncthreads();
+            // owner order: consecutive q of one owner -> consecutive addresses in its region (coalesced NVLink stores)
+            for (int q = threadIdx.x; q < m; q += SW_THREADS) {
+                uint32_t d = 0;
+#pragma unroll
+                for (int t = 1; t < 16; t++) d += s_off[t] <= (uint32_t)q;
+                const uint32_t bd = s_base[d];
+                if (bd != 0xFFFFFFFFu) s_peer[d][(size_t)bd + ((uint32_t)q - s_off[d])] = s_stage[s_inv[q]];
+            }
+        }
+        __syncthreads();  // s_piece / s_fwd / s_flags reuse in the next grid-stride iteration
     }
 }
 

@@ -21,6 +21,7 @@ on CPU tensors with a stand-in engine.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -144,17 +145,22 @@ class GpuEngine:
 
 class PeerExchange:
     """Receive / answer buffers of one rank, mapped into every other rank of the box with CUDA IPC, so that
-    the router kernel stores each word directly into its owner's memory over NVLink and the owner's probe
-    kernel stores each answer directly back (no send buffer, no NCCL data path).  The process group only
-    carries the g x g count matrix, the IPC handles and barriers, so it may be NCCL or gloo."""
+    the fused encode + necklace + route kernel stores each word directly into its owner's memory over NVLink
+    and the owner's probe kernel stores each answer directly back (no send buffer, no counting pass, no NCCL
+    data path).  The process group only carries per-batch counts, the IPC handles and barriers, so it may
+    be NCCL or gloo.
+
+    Layout: the receive buffer of owner d is ``world`` regions of ``cap`` words, region s written by rank s
+    only (slots reserved chunk by chunk with device-local atomics); the answer buffer of rank s is ``world``
+    regions of ``cap`` bytes, region d written by owner d only, answer j of region d belonging to word j of
+    region s at owner d."""
 
     def __init__(self, cbl, group, rank: int, world: int, device):
         self.cbl, self.group, self.rank, self.world, self.device = cbl, group, rank, world, device
         self.word_bytes = cbl.word_bytes()
         backend = dist.get_backend(group)
         self.ctrl = torch.device("cpu") if backend == "gloo" else device
-        self.cap_recv = 0   # words
-        self.cap_back = 0   # bytes
+        self.cap = 0        # words per region
         self.own_recv = self.own_back = 0
         self.peer_recv: List[int] = []
         self.peer_back: List[int] = []
@@ -166,8 +172,8 @@ class PeerExchange:
             dist.barrier(group=self.group, device_ids=[self.device.index])
 
     def all_counts(self, counts: np.ndarray) -> np.ndarray:
-        """g x g matrix C[s][d] = words rank s sends to rank d."""
-        mine = torch.from_numpy(counts.astype(np.int64)).to(self.ctrl)
+        """g x len(counts) matrix of every rank's vector; doubles as a barrier."""
+        mine = torch.from_numpy(np.ascontiguousarray(counts).astype(np.int64)).to(self.ctrl)
         out = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(out, mine, group=self.group)
         return torch.stack(out).cpu().numpy().astype(np.uint64)
@@ -187,25 +193,30 @@ class PeerExchange:
             self.cbl.peer_free(self.own_back)
         self.own_recv = self.own_back = 0
 
-    def ensure(self, need_recv_words: int, need_back_bytes: int):
-        """Collective: every rank calls it with the same arguments (they come from the count matrix)."""
-        if need_recv_words <= self.cap_recv and need_back_bytes <= self.cap_back and self.peer_recv:
+    def ensure(self, cap_words: int):
+        """Collective: every rank calls it with the same argument."""
+        if cap_words <= self.cap and self.peer_recv:
             return
         self._release()
-        self.cap_recv = max(int(need_recv_words * 1.25) + 1024, self.cap_recv)
-        self.cap_back = max(int(need_back_bytes * 1.25) + 1024, self.cap_back)
-        self.own_recv, h_recv = self.cbl.peer_alloc(self.cap_recv * self.word_bytes)
-        self.own_back, h_back = self.cbl.peer_alloc(self.cap_back)
+        self.cap = max((int(cap_words) + 2047) // 2048 * 2048, self.cap)
+        if self.world * self.cap >= 1 << 32:
+            raise ValueError("batch too large for one exchange: split the reads into smaller batches")
+        self.own_recv, h_recv = self.cbl.peer_alloc(self.world * self.cap * self.word_bytes)
+        self.own_back, h_back = self.cbl.peer_alloc(self.world * self.cap)
         handles = [None] * self.world
         dist.all_gather_object(handles, (h_recv, h_back), group=self.group)
         self.peer_recv = [self.own_recv if r == self.rank else self.cbl.peer_open(handles[r][0]) for r in range(self.world)]
         self.peer_back = [self.own_back if r == self.rank else self.cbl.peer_open(handles[r][1]) for r in range(self.world)]
         self.barrier()
 
+    def my_regions(self) -> List[int]:
+        """my region inside every owner's receive buffer"""
+        return [p + self.rank * self.cap * self.word_bytes for p in self.peer_recv]
+
     def close(self):
         if self.peer_recv or self.own_recv:
             self._release()
-        self.cap_recv = self.cap_back = 0
+        self.cap = 0
 
 
 class ShardedCBL:
@@ -238,8 +249,6 @@ class ShardedCBL:
         self.splitters_u32 = sp.cpu().numpy().astype(np.uint32)
         # data path of the exchange: "peer" = fused route + NVLink stores into the owner's buffers (default on
         # GPUs), "nccl" = partition into a send buffer + all_to_all_single (also what CPU stand-ins use)
-        import os
-
         mode = os.environ.get("CBL_EXCHANGE", "peer")
         self.peer = None
         if self.world > 1 and mode == "peer" and isinstance(self.engine, GpuEngine):
@@ -263,32 +272,37 @@ class ShardedCBL:
         recv, recv_counts = exchange(send, counts, self.group)
         return recv, pos, counts, recv_counts
 
-    def _peer_route(self, words: torch.Tensor, want_pos: bool):
-        """Fused route + exchange.  -> (count matrix C, pos tensor or None); this rank's received words are in
-        self.peer.own_recv, grouped by source rank."""
+    def _peer_route_seqs(self, d_buf: int, offsets: np.ndarray, want_pos: bool):
+        """Fused encode + necklace + route + exchange of this rank's reads.  -> (C, pos): C[s][d] = words rank s
+        stored into its region at owner d; pos (int32 device tensor or None) = answer slot of every local k-mer."""
         px, cbl = self.peer, self.engine.cbl
-        n = words.shape[0]
-        torch.cuda.current_stream(self.device).synchronize()
-        counts = cbl.route_counts_dev(words.data_ptr(), n, self.splitters_u32)
-        C = px.all_counts(counts)                                   # C[s][d]
-        px.ensure(int(C.sum(axis=0).max()), int(C.sum(axis=1).max()))  # ends with a barrier only when it reallocates
-        px.barrier()                                                # every owner is done with the previous batch
-        recv_offset = C[: self.rank, :].sum(axis=0)                 # my region inside each owner's buffer
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = cbl.count_kmers(offsets)
+        # doubles as the barrier "every rank is done with the buffers of the previous batch"
+        n_max = int(px.all_counts(np.array([n], dtype=np.uint64)).max())
+        cap = int(n_max / self.world * float(os.environ.get("CBL_ROUTE_SLACK", self.SLACK))) + 4096
         pos = torch.empty(n, dtype=torch.int32, device=self.device) if want_pos else None
-        cbl.route_scatter_dev(words.data_ptr(), n, self.splitters_u32, px.peer_recv, recv_offset, counts,
-                              pos.data_ptr() if want_pos else 0)
-        px.barrier()                                                # all words have landed
-        return C, pos
+        torch.cuda.current_stream(self.device).synchronize()
+        while True:
+            px.ensure(cap)
+            counts = cbl.seq_route_dev(d_buf, offsets, self.splitters_u32, px.my_regions(), px.cap, pos.data_ptr() if want_pos else 0)
+            C = px.all_counts(counts)                                # barrier: all words have landed
+            if int(C.max()) <= px.cap:
+                return C, pos
+            cap = int(int(C.max()) * 1.1) + 4096                     # a region overflowed somewhere: everybody retries
+
+    SLACK = 1.15   # region capacity over the even share (equal-mass splitters keep the spread at a few per cent)
 
     def _mutate(self, op: int, d_buf: int, offsets: np.ndarray) -> None:
-        words = self.engine.seq_words(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
         if self.peer is not None:
-            C, _ = self._peer_route(words, want_pos=False)
-            del words
-            n_recv = int(C[:, self.rank].sum())
-            if n_recv:
-                self.engine.cbl.words_op_dev(op, self.peer.own_recv, n_recv, 0)
+            px, cbl = self.peer, self.engine.cbl
+            C, _ = self._peer_route_seqs(d_buf, offsets, want_pos=False)
+            col = C[:, self.rank]
+            segs = [px.own_recv + s * px.cap * px.word_bytes for s in range(self.world)]
+            if int(col.sum()):
+                cbl.words_op_segments_dev(op, segs, col)
             return
+        words = self.engine.seq_words(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
         recv, _, _, _ = self._route_words(words)
         self.engine.words_op(op, recv, want_flags=False)
 
@@ -300,19 +314,6 @@ class ShardedCBL:
         self._mutate(2, d_buf, offsets)
 
     def contains_words(self, words: torch.Tensor) -> torch.Tensor:
-        if self.peer is not None:
-            px, cbl = self.peer, self.engine.cbl
-            n = words.shape[0]
-            C, pos = self._peer_route(words, want_pos=True)
-            col = C[:, self.rank]
-            src_begin = np.concatenate([[0], np.cumsum(col)]).astype(np.uint64)
-            back_offset = C[:, : self.rank].sum(axis=1)             # where my answers start inside each source's buffer
-            cbl.probe_words_scatter_dev(px.own_recv, int(col.sum()), src_begin, px.peer_back, back_offset)
-            px.barrier()                                            # all answers have landed
-            out = torch.empty(n, dtype=torch.uint8, device=self.device)
-            if n:
-                cbl.gather_u8_dev(px.own_back, pos.data_ptr(), n, out.data_ptr())
-            return out
         recv, pos, counts, recv_counts = self._route_words(words)
         flags = self.engine.words_op(0, recv, want_flags=True)
         if self.world > 1:
@@ -327,6 +328,19 @@ class ShardedCBL:
     def contains_seqs_dev(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
         """Per-k-mer answers (uint8 device tensor) for this rank's reads, in the reference's order
         (src/cbl.rs:311-324)."""
+        if self.peer is not None:
+            px, cbl = self.peer, self.engine.cbl
+            C, pos = self._peer_route_seqs(d_buf, offsets, want_pos=True)
+            for s in range(self.world):   # region s of my receive buffer -> my region of rank s's answer buffer
+                n_s = int(C[s, self.rank])
+                if n_s:
+                    cbl.words_op_dev(0, px.own_recv + s * px.cap * px.word_bytes, n_s, px.peer_back[s] + self.rank * px.cap)
+            px.barrier()                                            # all answers have landed
+            n = pos.shape[0]
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+            if n:
+                cbl.gather_u8_dev(px.own_back, pos.data_ptr(), n, out.data_ptr())
+            return out
         words = self.engine.seq_words(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
         return self.contains_words(words)
 

@@ -104,8 +104,12 @@ int32_t cbl_load_from_file(const cbl_t* proto, const char* path, cbl_t** out);
  *      all-to-all that routes each word to the GPU owning its prefix range ----------- */
 /* words of the records, in the reference's order, left on the device: d_words = n_kmers * (8|16) bytes */
 int32_t cbl_seq_words_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, void* d_words);
-/* op: 0 contains (d_out required), 1 insert, 2 remove (d_out optional = membership before the call) */
+/* op: 0 contains (d_out required), 1 insert, 2 remove (d_out optional = membership before the call);
+ * d_out may be peer memory (the sharded path answers straight into the asking rank's buffer) */
 int32_t cbl_words_op_dev(cbl_t* h, int32_t op, const void* d_words, size_t n, uint8_t* d_out);
+/* insert (1) / remove (2) the words of n_seg device segments as ONE batch (the per-source regions of a sharded receive
+ * buffer): the shard is rewritten once, not once per segment */
+int32_t cbl_words_op_segments_dev(cbl_t* h, int32_t op, const void* const* seg, const uint64_t* seg_n, uint32_t n_seg);
 int32_t cbl_export_words_dev(cbl_t* h, uint64_t start, uint64_t count, void* d_out);
 /* router: stable partition of n words by owner rank, dest = number of splitters <= prefix (contiguous
  * prefix ranges).  d_send: the words grouped by destination; d_pos (may be NULL): for every input word
@@ -130,10 +134,16 @@ int32_t cbl_route_counts_dev(cbl_t* h, const void* d_words, size_t n, const uint
  * destination-major send order (what cbl_gather_u8_dev needs).  Returns when the stores are complete. */
 int32_t cbl_route_scatter_dev(cbl_t* h, const void* d_words, size_t n, const uint32_t* splitters, uint32_t n_splitters,
                               void* const* peer_recv, const uint64_t* recv_offset, const uint64_t* counts, uint32_t* d_pos);
-/* membership of n received words; words [src_begin[s], src_begin[s+1]) came from rank s and answer j of that
- * range is stored to peer_back[s][back_offset[s] + j].  n_src <= 16.  Returns when the stores are complete. */
-int32_t cbl_probe_words_scatter_dev(cbl_t* h, const void* d_words, size_t n, uint32_t n_src, const uint64_t* src_begin,
-                                    uint8_t* const* peer_back, const uint64_t* back_offset);
+/* ONE kernel for "reads -> words -> owner": fused 2-bit encode + necklace + route (src/cbl.rs:247-289 plus the
+ * all-to-all of the sharded design).  Every word of the records is stored straight into peer_region[d], THIS rank's
+ * region (cap words, 16-byte aligned) inside owner d's receive buffer; space is reserved chunk by chunk, so the order
+ * inside a region is arbitrary.  counts[d] (host, n_splitters+1) = words sent to d; counts[d] > cap means the region
+ * overflowed (nothing was written past cap): retry the call with a larger cap.  d_pos (may be NULL): for k-mer i (the
+ * reference's order) d * cap + its index inside region d, i.e. where its answer comes back when every owner
+ * answers region s of its receive buffer into region (owner rank) of rank s's answer buffer (cbl_words_op_dev with
+ * d_out = that peer pointer).  (n_splitters+1) * cap < 2^32.  Returns when the stores are complete. */
+int32_t cbl_seq_route_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, const uint32_t* splitters,
+                          uint32_t n_splitters, void* const* peer_region, uint64_t cap, uint32_t* d_pos, uint64_t* counts);
 int32_t cbl_word_bytes(const cbl_t* h, int32_t* out);      /* 8 or 16: size of one device word */
 int32_t cbl_suffix_bits(const cbl_t* h, int32_t* out);
 
