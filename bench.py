@@ -104,24 +104,74 @@ def make_workload(torch, device, index_bp: int, query_bp: int, rec: int, seed_ba
 # clocks during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: an in-process NVML thread (5 ms period; the
+    timed region of this bench is tens of milliseconds, too short for an `nvidia-smi -lms` child to start up),
+    falling back to `nvidia-smi -lms` when NVML is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc = [], None
+    def __init__(self, gpu_index: int, uuid: str | None = None):
+        self.rows, self.proc, self.nv, self.samples = [], None, None, []
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv, self.h = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                except Exception:
+                    pw = None
+                self.samples.append((mhz, rs, pw))
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            nv = self.nv
+            flags = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+                     "hw_power_brake_slowdown": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+            reasons = sorted(k for k, f in flags.items() if any(rs & f for _, rs, _ in self.samples))
+            sm = [m for m, _, _ in self.samples]
+            pw = [p for _, _, p in self.samples if p is not None]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "power_w_max": max(pw) if pw else None, "source": "nvml, 5 ms period, timed region only"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -144,7 +194,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -282,7 +332,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, str(torch.cuda.get_device_properties(local).uuid)) if rank == 0 else None
     launches0 = cbl_b200.launch_count()
     cbl_b200.profile_enable(True)
     cbl_b200.profile_report()

@@ -495,6 +495,10 @@ int32_t cbl_profile_report(char* out, size_t cap) {
         memcpy(out, r.c_str(), r.size() + 1);
     });
 }
+int32_t cbl_mem_trim(int32_t device) {
+    return guard(nullptr, [&] { CUDA_CHECK(cudaSetDevice(device)); arena::trim(); });
+}
+uint64_t cbl_mem_cached_bytes(void) { return arena::cached_bytes(); }
 const char* cbl_build_info(void) { return "libcbl_gpu sm_100a (cuda " CBL_STR(CUDART_VERSION) ")"; }
 
 }  // extern "C"

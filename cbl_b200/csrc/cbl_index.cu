@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <unordered_map>
 
 #include "index_ops.cuh"
 #include "merge_ops.cuh"
@@ -54,6 +55,116 @@ std::string prof_report() {
     }
     return out + "}";
 }
+
+// ------------------------------------------------------------------------------------------------
+// device memory arena (see common.cuh)
+// ------------------------------------------------------------------------------------------------
+namespace arena {
+namespace {
+struct Block { size_t bytes; int device; };
+struct State {
+    std::mutex mu;
+    std::unordered_map<void*, Block> live;                                         // every block handed out
+    std::map<std::pair<int, cudaStream_t>, std::multimap<size_t, void*>> by_stream; // free, reusable on that stream
+    std::map<int, std::multimap<size_t, void*>> idle;                               // free, reusable anywhere on the device
+    std::unordered_map<void*, Block> cached;                                       // blocks sitting in a free list
+    uint64_t cached_bytes = 0;
+    int mode = -1;                                                                 // 1 arena, 0 cudaMallocAsync
+};
+State& st() { static State* s = new State; return *s; }   // leaked on purpose: CUDA may be gone at static destruction
+bool enabled(State& S) {
+    if (S.mode < 0) { const char* e = getenv("CBL_ARENA"); S.mode = (e && e[0] == '0') ? 0 : 1; }
+    return S.mode == 1;
+}
+size_t size_class(size_t b) {
+    if (b < 512) return 512;
+    const int top = 63 - __builtin_clzll(b);
+    if (b <= (1u << 20)) return (b & (b - 1)) ? (size_t)1 << (top + 1) : b;        // power of two up to 1 MB
+    const size_t step = (size_t)1 << (top - 3);                                    // 8 classes per octave above
+    return (b + step - 1) / step * step;
+}
+void* take(std::multimap<size_t, void*>& m, size_t need, size_t limit) {
+    auto it = m.lower_bound(need);
+    if (it == m.end() || it->first > limit) return nullptr;
+    void* p = it->second;
+    m.erase(it);
+    return p;
+}
+void trim_locked(State& S, int dev) {
+    cudaDeviceSynchronize();
+    for (auto it = S.by_stream.begin(); it != S.by_stream.end(); ++it)
+        if (it->first.first == dev) { for (auto& kv : it->second) { S.cached_bytes -= kv.first; S.cached.erase(kv.second); cudaFree(kv.second); } it->second.clear(); }
+    auto& idle = S.idle[dev];
+    for (auto& kv : idle) { S.cached_bytes -= kv.first; S.cached.erase(kv.second); cudaFree(kv.second); }
+    idle.clear();
+}
+}  // namespace
+
+void* alloc(size_t bytes, cudaStream_t s) {
+    State& S = st();
+    std::lock_guard<std::mutex> lk(S.mu);
+    if (!enabled(S)) {
+        void* p = nullptr;
+        CUDA_CHECK(cudaMallocAsync(&p, bytes, s));
+        return p;
+    }
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    const size_t need = size_class(bytes);
+    const size_t limit = need <= (1u << 20) ? need * 2 : need + need / 2;
+    void* p = take(S.by_stream[{dev, s}], need, limit);
+    if (!p) p = take(S.idle[dev], need, limit);
+    if (p) {
+        auto it = S.cached.find(p);
+        S.cached_bytes -= it->second.bytes;
+        S.live[p] = it->second;
+        S.cached.erase(it);
+        return p;
+    }
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaErrorMemoryAllocation) {  // give the cache back and try once more
+        cudaGetLastError();
+        trim_locked(S, dev);
+        e = cudaMalloc(&p, need);
+    }
+    CUDA_CHECK(e);
+    S.live[p] = Block{need, dev};
+    return p;
+}
+void release(void* p, cudaStream_t s) {
+    State& S = st();
+    std::lock_guard<std::mutex> lk(S.mu);
+    auto it = S.live.find(p);
+    if (it == S.live.end()) { cudaFreeAsync(p, s); return; }   // allocated in cudaMallocAsync mode
+    const Block b = it->second;
+    S.live.erase(it);
+    S.cached[p] = b;
+    S.cached_bytes += b.bytes;
+    S.by_stream[{b.device, s}].emplace(b.bytes, p);
+}
+void retire_stream(cudaStream_t s) {
+    State& S = st();
+    std::lock_guard<std::mutex> lk(S.mu);
+    for (auto it = S.by_stream.begin(); it != S.by_stream.end();) {
+        if (it->first.second == s) {
+            auto& idle = S.idle[it->first.first];
+            for (auto& kv : it->second) idle.emplace(kv.first, kv.second);
+            it = S.by_stream.erase(it);
+        } else ++it;
+    }
+}
+void trim() {
+    State& S = st();
+    std::lock_guard<std::mutex> lk(S.mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) trim_locked(S, dev);
+}
+uint64_t cached_bytes() {
+    State& S = st();
+    std::lock_guard<std::mutex> lk(S.mu);
+    return S.cached_bytes;
+}
+}  // namespace arena
 
 static int pos_bits_for(int kmer_bits) {  // src/cbl.rs:66
     int p = 0;
@@ -163,8 +274,8 @@ public:
     ~Index() override {
         cudaSetDevice(cfg_.device);
         dir_.release(); bucket_range_.release(); bucket_prefix_.release(); bucket_off_.release(); suf_.release(); sub_.release();
-        if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
-        for (auto& s : side_) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+        if (st_) { cudaStreamSynchronize(st_); arena::retire_stream(st_); cudaStreamDestroy(st_); }
+        for (auto& s : side_) if (s) { cudaStreamSynchronize(s); arena::retire_stream(s); cudaStreamDestroy(s); }
     }
 
     const Config& config() const override { return cfg_; }
@@ -541,12 +652,16 @@ public:
         Trace tr(st_);
         W* sorted = sort_keys(a, b, n);
         tr.mark("  sort enqueue");
-        W* other = sorted == a ? b : a;
-        uint64_t nu = unique_keys(sorted, n, other);
-        tr.mark("  unique (sync inside)");
         NewState ns;
-        if (use_merge_) merge_new_state(other, nu, mode == EDIT_INS ? MERGE_OR : MERGE_SUB, ns);
-        else compute_new_state(other, nu, mode, view(), sorted, ns);
+        if (use_merge_) {
+            // the merge treats a repeated batch word as one (merge_ops.cuh): no unique pass, no count read-back
+            merge_new_state(sorted, n, mode == EDIT_INS ? MERGE_OR : MERGE_SUB, ns);
+        } else {
+            W* other = sorted == a ? b : a;
+            uint64_t nu = unique_keys(sorted, n, other);
+            tr.mark("  unique (sync inside)");
+            compute_new_state(other, nu, mode, view(), sorted, ns);
+        }
         tr.mark("  new state (syncs inside)");
         if (ns.changed) adopt(ns);
         tr.mark("  adopt");
@@ -693,7 +808,7 @@ public:
                     if (sl[i].s) cudaStreamSynchronize(sl[i].s);
                     sl[i].free_host();
                     if (sl[i].done) cudaEventDestroy(sl[i].done);
-                    if (sl[i].s) cudaStreamDestroy(sl[i].s);
+                    if (sl[i].s) { arena::retire_stream(sl[i].s); cudaStreamDestroy(sl[i].s); }
                 }
             }
         } cleanup{slots};

@@ -1,7 +1,8 @@
 // Kernels k4-k7 (second generation): every mutation of a shard — insert_seq, remove_seq, | & - ^ — is ONE
 // streaming merge of two ascending word sequences:
 //     A = the resident index (CSR: prefix of the bucket, suffix of the element), never materialised as words
-//     B = the batch (sorted, distinct words; for set operations the other index expanded)
+//     B = the batch (sorted words, duplicates allowed: a repeated word counts once, so the sort needs no
+//         separate unique pass; for set operations the other index expanded)
 // Replaces WordSet::insert_batch / remove_batch (src/wordset/mod.rs:187-237) and the binary set
 // operations (src/wordset/set_ops.rs:78-410, src/trievec/set_ops.rs:5-257, src/bitvector/set_ops.rs:4-106).
 //
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_excl;
     __shared__ uint32_t s_tmp[33];
+    __shared__ W s_bprev;                                   // B[j0 - 1]: a B element equal to its predecessor is a repeat
     const W SENTINEL = ~(W)0;  // no word is all ones (the position field of an all-ones necklace is 0)
     constexpr uint32_t NONE = 0xFFFFFFFFu;
 
@@ -103,13 +105,19 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     }
     __syncthreads();
     // ---- stage A words and B words (coalesced global reads, consecutive shared slots) ----
-    for (int s = threadIdx.x; s < na; s += MG_THREADS) {
-        int lo = 0, hi = n_bk;                                 // last bucket with start <= s
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if ((int)s_pos[mid] <= s) lo = mid; else hi = mid;
+    {
+        int lo = 0;                                            // last bucket with start <= s; s grows, so lo never moves back
+        for (int s = threadIdx.x; s < na; s += MG_THREADS) {
+            if (lo + 1 < n_bk && (int)s_pos[lo + 1] <= s) {    // usually false: 256 elements rarely leave a bucket
+                int hi = n_bk;
+                lo++;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((int)s_pos[mid] <= s) lo = mid; else hi = mid;
+                }
+            }
+            sK[1 + s] = (W)(((W)s_pfx[lo] << P.suffix_bits) | (W)ix.suf[i0 + s]);
         }
-        sK[1 + s] = (W)(((W)s_pfx[lo] << P.suffix_bits) | (W)ix.suf[i0 + s]);
     }
     for (int s = threadIdx.x; s < nb; s += MG_THREADS) sK[1 + na + s] = B[j0 + s];
     if (threadIdx.x == 0) {
@@ -120,6 +128,7 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
         }
         sK[0] = h;
         sK[1 + na + nb] = j1 < nB ? B[j1] : SENTINEL;
+        s_bprev = j0 > 0 ? B[j0 - 1] : SENTINEL;
     }
     __syncthreads();
 
@@ -135,26 +144,34 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     int ia = lo, ib = d - lo;
     W out[MG_ITEMS];
     uint32_t emit_mask = 0;
+    {
+        // the current and the previous element of both sides live in registers: one shared load per step
+        W a = ia < na ? sA[ia] : SENTINEL;
+        W b = sB[ib];                                  // ib == nb reads the B halo
+        W pa = sA[ia - 1];                             // the largest A element taken so far (A halo when ia == 0)
+        W pb = ib > 0 ? sB[ib - 1] : s_bprev;          // a B element equal to its predecessor is a repeat
 #pragma unroll
-    for (int e = 0; e < MG_ITEMS; e++) {
-        out[e] = 0;
-        if (ia + ib < na + nb) {
-            const W a = ia < na ? sA[ia] : SENTINEL;
-            const W b = sB[ib];                        // ib == nb reads the B halo
-            const bool take_a = ia < na && (ib >= nb || a <= b);
-            bool emit;
-            if (take_a) {
-                const bool eq_b = b == a;              // b is the smallest B element >= a
-                emit = OP == MERGE_OR ? true : OP == MERGE_AND ? eq_b : !eq_b;
-                out[e] = a;
-                ia++;
-            } else {
-                const bool eq_a = sA[ia - 1] == b;     // the largest A element <= b (A halo when ia == 0)
-                emit = (OP == MERGE_OR || OP == MERGE_XOR) && !eq_a;
-                out[e] = b;
-                ib++;
+        for (int e = 0; e < MG_ITEMS; e++) {
+            out[e] = 0;
+            if (ia + ib < na + nb) {
+                const bool take_a = ia < na && (ib >= nb || a <= b);
+                bool emit;
+                if (take_a) {
+                    const bool eq_b = b == a;          // b is the smallest B element >= a
+                    emit = OP == MERGE_OR ? true : OP == MERGE_AND ? eq_b : !eq_b;
+                    out[e] = a;
+                    pa = a;
+                    ia++;
+                    a = ia < na ? sA[ia] : SENTINEL;
+                } else {
+                    emit = (OP == MERGE_OR || OP == MERGE_XOR) && pa != b && pb != b;
+                    out[e] = b;
+                    pb = b;
+                    ib++;
+                    b = sB[ib];
+                }
+                emit_mask |= (emit ? 1u : 0u) << e;
             }
-            emit_mask |= (emit ? 1u : 0u) << e;
         }
     }
     // ---- prefix runs: a head is an emitted element whose prefix differs from the previously emitted one ----
@@ -186,7 +203,8 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     const uint32_t packed = block_excl_scan<uint32_t, MG_THREADS>(__popc(emit_mask) | (__popc(hm) << 16), s_tmp, packed_tot);
     const uint32_t off = packed & 0xFFFFu, tile_emitted = packed_tot & 0xFFFFu, n_heads = packed_tot >> 16;
     uint32_t hoff = packed >> 16;
-    const uint64_t excl = block_lookback(status, tile, tile_emitted, &s_excl);
+    // publish the tile's count at once, stage the output while the predecessors finish, resolve the prefix last
+    if (threadIdx.x == 0) lookback_publish(status, tile, tile_emitted);
     {
         uint32_t k = off;
 #pragma unroll
@@ -197,7 +215,12 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
                 k++;
             }
     }
+    if (threadIdx.x < 32) {
+        const uint64_t e = lookback_resolve(status, tile, tile_emitted);
+        if (threadIdx.x == 0) s_excl = e;
+    }
     __syncthreads();
+    const uint64_t excl = s_excl;
     for (uint32_t k = threadIdx.x; k < tile_emitted; k += MG_THREADS) suf_out[excl + k] = s_out[mg_pad(k)];
     for (uint32_t h = threadIdx.x; h < n_heads; h += MG_THREADS) {
         const uint32_t p0 = s_pos[h], p1 = h + 1 < n_heads ? s_pos[h + 1] : tile_emitted;

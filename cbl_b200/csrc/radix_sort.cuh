@@ -9,6 +9,9 @@
 
 namespace cbl {
 
+#ifndef CBL_RS_ABLATE
+#define CBL_RS_ABLATE 0   // developer ablations: 1 = no look-back, 2 = no peer detection (wrong results, timing only)
+#endif
 #ifndef CBL_RS_MIN_BLOCKS
 #define CBL_RS_MIN_BLOCKS 4
 #endif
@@ -107,16 +110,174 @@ __global__ void __launch_bounds__(256) radix_scan_hist_kernel(unsigned long long
 }
 
 // One scatter pass.  status[tile][256] must be zero on entry; tile_counter zero.
-// HAS_VAL: a u32 payload travels with every key.  pos_out (may be null): receives, for every input
-// slot, the slot its key was moved to (used by the multi-GPU router to bring answers back).
+// pos_out (may be null): receives, for every input slot, the slot its key was moved to (used by the multi-GPU
+// router to bring answers back).  HAS_VAL is kept in the signature for the call sites; no payload variant exists.
 //
-// Ranking (stable): all match_any's of a thread are issued back to back, then the highest lane of
-// every peer group adds the group size to its warp's digit counter (shared atomic, returns the base)
-// and broadcasts it; the atomics of one warp execute in program order, which keeps items ordered.
-// Tile prefixes: decoupled look-back, one thread per digit.
+// Stable ranking of a row (the 32 keys one warp instruction holds) on B200: match.any costs ~60 SM-cycles per warp
+// when the digits differ, a shared atomic ~4 (measured, scripts/ubench), so the lanes with equal digits find each
+// other through shared memory: every lane ORs its bit into mask[digit] and reads the word back = its peer group.
+// The highest lane of a group reserves the group's slots in the warp's digit counter (one shared atomicAdd per
+// group, rows in program order => stable) and broadcasts the base.  Three mask sets rotate so that one warp barrier
+// per row is enough: every lane clears the word it used two rows ago.
+// The body is compiled twice (FULL tile / ragged last tile): the full-tile copy carries no bounds predicates, all
+// offsets are 32-bit, and nothing but (rank | digit << 16) is kept per key between the phases (the first version
+// executed ~140 SASS instructions per row and spilled; this one ~45).
+// Tile prefixes: decoupled look-back, one thread per digit, 8 predecessor tiles per round trip.
 //
 // MULTI_OUT (router only): digit d's keys go to peers.p[d][digit_base[d] + ...] instead of out[...], and
 // pos_out receives local_base[d] + rank of the key among this rank's keys for d (its slot in send order).
+template <class W, class DigitFn, bool MULTI_OUT, bool FULL>
+__device__ __forceinline__ void radix_tile(const W* __restrict__ in, W* __restrict__ out, uint64_t n, const DigitFn& digit,
+                                           const unsigned long long* __restrict__ digit_base, volatile uint32_t* status,
+                                           uint32_t* __restrict__ pos_out, const unsigned long long* __restrict__ local_base,
+                                           const uint32_t tile, W* s_keys, uint32_t (*s_whist)[256], long long* s_goff64, uint32_t* s_goff32,
+                                           long long* s_loff, W** s_outp, uint32_t* s_tmp) {
+    constexpr int ITEMS = RsTile<W>::ITEMS;
+    constexpr int TILE = RsTile<W>::TILE;
+    const uint64_t tile_base = (uint64_t)tile * TILE;
+    const int tile_n = FULL ? TILE : (int)(n - tile_base);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = threadIdx.x;
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_keys);   // the key staging area is free until step 5
+
+    // 0. zero the warp histograms and the mask sets (vector stores)
+    {
+        uint4* z = reinterpret_cast<uint4*>(&s_whist[0][0]);
+#pragma unroll
+        for (int i = 0; i < RS_WARPS * 256 / 4 / RS_THREADS; i++) z[i * RS_THREADS + t] = make_uint4(0, 0, 0, 0);
+        uint4* zm = reinterpret_cast<uint4*>(s_mask);
+#pragma unroll
+        for (int i = 0; i < 3 * RS_WARPS * 256 / 4 / RS_THREADS; i++) zm[i * RS_THREADS + t] = make_uint4(0, 0, 0, 0);
+    }
+    // 1. load (warp-striped: order = warp, item, lane)
+    W key[ITEMS];
+    const W* src = in + tile_base + warp * (32 * ITEMS) + lane;
+    const int local0 = warp * (32 * ITEMS) + lane;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) key[i] = (FULL || local0 + i * 32 < tile_n) ? src[i * 32] : (W)0;
+    __syncthreads();  // s_whist / s_mask zeroed
+
+    // 2 + 3. peer group of every row, group leaders reserve slots; rd = rank inside (warp, digit) | digit << 16
+    uint32_t rd[ITEMS];
+    {
+        uint32_t* const Mw = s_mask + warp * 256;
+        uint32_t* const Hw = &s_whist[warp][0];
+        const uint32_t lanebit = 1u << lane, ltmask = lanebit - 1u;
+        uint32_t *a1 = Mw, *a2 = Mw;
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const bool valid = FULL || local0 + i * 32 < tile_n;
+            const uint32_t d = digit(key[i]);
+            uint32_t* const a = Mw + (i % 3) * (RS_WARPS * 256) + d;
+#if CBL_RS_ABLATE == 2
+            const uint32_t peers = lanebit;
+#else
+            if (valid) atomicOr(a, lanebit);
+            __syncwarp();
+            const uint32_t peers = valid ? *reinterpret_cast<volatile uint32_t*>(a) : lanebit;
+            if (i >= 2) *reinterpret_cast<volatile uint32_t*>(a2) = 0u;   // every lane of a group clears the same word
+#endif
+            a2 = a1;
+            a1 = a;
+            uint32_t base = 0;
+            if (valid && (peers >> lane) == 1u) base = atomicAdd(Hw + d, (uint32_t)__popc(peers));   // highest lane of the group
+            base = __shfl_sync(0xffffffffu, base, 31 - __clz(peers));
+            rd[i] = (base + __popc(peers & ltmask)) | (d << 16);
+        }
+    }
+    __syncthreads();
+
+    // 4a. per digit (thread t = digit t): tile count (published at once as this tile's aggregate), exclusive
+    //     offsets over warps
+    uint32_t run = 0, dstart;
+    {
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) run += s_whist[w][t];
+        if (tile == 0) status[t] = RS_FLAG_INCL | run;
+        else status[(size_t)tile * 256 + t] = RS_FLAG_AGG | run;
+        uint32_t total;
+        dstart = block_excl_scan<uint32_t, RS_THREADS>(run, s_tmp, total);
+        uint32_t acc = dstart;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) { const uint32_t c = s_whist[w][t]; s_whist[w][t] = acc; acc += c; }   // slot of (warp, digit) in the tile
+    }
+    __syncthreads();
+
+    // 5. local scatter into digit order (before the look-back wait: the keys leave the registers)
+    {
+        const uint32_t* const Hw = &s_whist[warp][0];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            if (FULL || local0 + i * 32 < tile_n) {
+                const uint32_t d = rd[i] >> 16;
+                const uint32_t pos = Hw[d] + (rd[i] & 0xFFFFu);
+                s_keys[pos] = key[i];
+                rd[i] = pos | (d << 16);
+            }
+        }
+    }
+
+    // 4b. decoupled look-back, LB predecessors per round trip (with ~600 resident tiles the nearest tile whose
+    //     inclusive prefix is published is typically tens of tiles back; one dependent L2 load per step was slow)
+    {
+        constexpr int LB = 8;
+        uint32_t excl = 0;
+        if (tile > 0 && CBL_RS_ABLATE != 1) {
+            long long prev = (long long)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t sv[LB];
+#pragma unroll
+                for (int j = 0; j < LB; j++) {
+                    uint32_t v0 = 2u << 30;   // virtual tile before the first: inclusive prefix 0
+                    if (prev - j >= 0) v0 = status[(size_t)(prev - j) * 256 + t];
+                    sv[j] = v0;
+                }
+#pragma unroll
+                for (int j = 0; j < LB; j++) {
+                    if (!done) {
+                        uint32_t v = sv[j];
+                        while ((v >> 30) == 0) v = status[(size_t)(prev - j) * 256 + t];
+                        excl += v & RS_VAL_MASK;
+                        done = (v & RS_FLAG_INCL) != 0;
+                    }
+                }
+                prev -= LB;
+            }
+            status[(size_t)tile * 256 + t] = RS_FLAG_INCL | (excl + run);
+        }
+        if (MULTI_OUT) {
+            s_goff64[t] = (long long)digit_base[t] + (long long)excl - (long long)dstart;
+            if (t <= ROUTE_MAX_SPLIT) s_loff[t] = (long long)local_base[t] + (long long)excl - (long long)dstart;
+        } else {
+            s_goff32[t] = (uint32_t)digit_base[t] + excl - dstart;   // n < 2^30: slots fit 32 bits (wrapping arithmetic)
+        }
+    }
+    __syncthreads();
+    if (DigitFn::WANTS_POS && pos_out != nullptr) {
+        uint32_t* const po = pos_out + tile_base + local0;
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            if (FULL || local0 + i * 32 < tile_n) {
+                const uint32_t d = rd[i] >> 16, pos = rd[i] & 0xFFFFu;
+                po[i * 32] = MULTI_OUT ? (uint32_t)(s_loff[d] + (long long)pos) : s_goff32[d] + pos;
+            }
+        }
+    }
+
+    // 6. coalesced global scatter: consecutive smem slots of one digit go to consecutive addresses
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const int idx = i * RS_THREADS + t;
+        if (FULL || idx < tile_n) {
+            const W k = s_keys[idx];
+            const uint32_t d = digit(k);
+            if (MULTI_OUT) s_outp[d][s_goff64[d] + idx] = k;
+            else out[s_goff32[d] + (uint32_t)idx] = k;
+        }
+    }
+}
+
 template <class W, bool HAS_VAL, class DigitFn, bool MULTI_OUT = false>
 __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kernel(const W* __restrict__ in, W* __restrict__ out,
                                                                    const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
@@ -124,13 +285,14 @@ __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kern
                                                                    volatile uint32_t* status, uint32_t* tile_counter,
                                                                    uint32_t* __restrict__ pos_out, PeerOuts peers = PeerOuts(),
                                                                    const unsigned long long* __restrict__ local_base = nullptr) {
-    constexpr int ITEMS = RsTile<W>::ITEMS;
+    static_assert(!HAS_VAL, "no payload variant");
+    static_assert(RsTile<W>::TILE <= 65536 && sizeof(W) * RsTile<W>::TILE >= 3 * RS_WARPS * 256 * 4, "tile / mask aliasing");
     constexpr int TILE = RsTile<W>::TILE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     W* s_keys = reinterpret_cast<W*>(smem_raw);
-    uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + sizeof(W) * TILE);  // only if HAS_VAL
-    __shared__ uint32_t s_whist[RS_WARPS][256];
-    __shared__ long long s_goff[256];
+    __shared__ __align__(16) uint32_t s_whist[RS_WARPS][256];
+    __shared__ long long s_goff64[MULTI_OUT ? 256 : 1];
+    __shared__ uint32_t s_goff32[MULTI_OUT ? 1 : 256];
     __shared__ long long s_loff[MULTI_OUT ? ROUTE_MAX_SPLIT + 1 : 1];
     __shared__ W* s_outp[MULTI_OUT ? ROUTE_MAX_SPLIT + 1 : 1];
     __shared__ uint32_t s_tmp[33];
@@ -138,124 +300,12 @@ __global__ void __launch_bounds__(RS_THREADS, CBL_RS_MIN_BLOCKS) radix_pass_kern
 
     if (MULTI_OUT && threadIdx.x <= ROUTE_MAX_SPLIT) s_outp[threadIdx.x] = reinterpret_cast<W*>(peers.p[threadIdx.x]);
     const uint32_t tile = block_ticket(tile_counter, &s_tile);
-    const uint64_t tile_base = (uint64_t)tile * TILE;
-    const int tile_n = (int)min((uint64_t)TILE, n - tile_base);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&s_whist[0][0])[i] = 0;
-    // peer masks (3 round-robin sets of [warp][256] words) live in the key staging area, which is not
-    // needed before step 5
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw);
-    for (int i = threadIdx.x; i < 3 * RS_WARPS * 256 / 4; i += RS_THREADS) reinterpret_cast<uint4*>(s_mask)[i] = make_uint4(0, 0, 0, 0);
-
-    // 1. load (warp-striped: order = warp, item, lane)
-    W key[ITEMS];
-    uint32_t val[ITEMS];
-    const bool full = tile_n == TILE;
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const int local = warp * (32 * ITEMS) + i * 32 + lane;
-        const bool valid = full || local < tile_n;
-        key[i] = valid ? in[tile_base + local] : (W)0;
-        if (HAS_VAL) val[i] = valid ? vin[tile_base + local] : 0u;
-    }
-    __syncthreads();  // s_whist / s_mask zeroed
-    // 2. peer groups of every row (the lanes of the warp holding the same digit), found through shared
-    //    memory: every lane ORs its bit into mask[digit], then reads the word back (match.any costs ~60
-    //    SM-cycles per warp on B200 when the digits are all different, a shared atomic ~4; measured).
-    //    Set i % 3 is cleaned by the leaders two rows later, which needs only one warp barrier per row.
-    //    info = rank inside the group (5 bits) | group size << 5 (6 bits) | leader lane << 11 (5 bits);
-    //    step 3 adds the group's base << 16 and finally turns info into the rank inside (warp, digit)
-    uint32_t info[ITEMS];
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const int local = warp * (32 * ITEMS) + i * 32 + lane;
-        const bool valid = full || local < tile_n;
-        uint32_t* M = s_mask + ((i % 3) * RS_WARPS + warp) * 256;
-        if (i >= 2) {
-            uint32_t* M2 = s_mask + (((i - 2) % 3) * RS_WARPS + warp) * 256;
-            if ((int)((info[i - 2] >> 11) & 31u) == lane) M2[digit(key[i - 2])] = 0;
-        }
-        const uint32_t d = digit(key[i]);
-#if CBL_RS_ABLATE == 2
-        const unsigned peers = 1u << lane;
-#else
-        if (valid) atomicOr(&M[d], 1u << lane);
-        __syncwarp();
-        const unsigned peers = valid ? M[d] : (1u << lane);
-#endif
-        info[i] = __popc(peers & lanemask_lt()) | (__popc(peers) << 5) | ((31 - __clz(peers)) << 11);
-    }
-    // 3. leaders reserve their group's slots in the warp histogram (in item order)
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const int local = warp * (32 * ITEMS) + i * 32 + lane;
-        const bool valid = full || local < tile_n;
-        if (valid && (int)((info[i] >> 11) & 31u) == lane) info[i] |= atomicAdd(&s_whist[warp][digit(key[i])], (info[i] >> 5) & 63u) << 16;
-    }
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) info[i] = __shfl_sync(0xffffffffu, info[i] >> 16, (info[i] >> 11) & 31u) + (info[i] & 31u);
-    __syncthreads();
-
-    // 4. per digit (thread t = digit t): exclusive offsets over warps, tile count, look-back
-    {
-        const int t = threadIdx.x;
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) run += s_whist[w][t];
-        if (tile == 0) status[t] = RS_FLAG_INCL | run;
-        else status[(size_t)tile * 256 + t] = RS_FLAG_AGG | run;
-        uint32_t total;
-        const uint32_t dstart = block_excl_scan<uint32_t, RS_THREADS>(run, s_tmp, total);
-        uint32_t acc = dstart;
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) { const uint32_t c = s_whist[w][t]; s_whist[w][t] = acc; acc += c; }   // slot of (warp, digit) in the tile
-        uint32_t excl = 0;
-#ifndef CBL_RS_ABLATE
-#define CBL_RS_ABLATE 0
-#endif
-        if (tile > 0 && CBL_RS_ABLATE != 1) {
-            for (long long prev = (long long)tile - 1; prev >= 0; prev--) {
-                uint32_t s;
-                do { s = status[(size_t)prev * 256 + t]; } while ((s >> 30) == 0);
-                excl += s & RS_VAL_MASK;
-                if (s & RS_FLAG_INCL) break;
-            }
-            status[(size_t)tile * 256 + t] = RS_FLAG_INCL | (excl + run);
-        }
-        s_goff[t] = (long long)digit_base[t] + (long long)excl - (long long)dstart;
-        if (MULTI_OUT && t <= ROUTE_MAX_SPLIT) s_loff[t] = (long long)local_base[t] + (long long)excl - (long long)dstart;
-    }
-    __syncthreads();
-
-    // 5. local scatter into digit order
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const int local = warp * (32 * ITEMS) + i * 32 + lane;
-        if (full || local < tile_n) {
-            const uint32_t d = digit(key[i]);
-            const uint32_t pos = s_whist[warp][d] + info[i];
-            s_keys[pos] = key[i];
-            if (HAS_VAL) s_vals[pos] = val[i];
-            if (DigitFn::WANTS_POS && pos_out != nullptr)
-                pos_out[tile_base + local] = (uint32_t)((MULTI_OUT ? s_loff[d] : s_goff[d]) + (long long)pos);
-        }
-    }
-    __syncthreads();
-
-    // 6. coalesced global scatter: consecutive smem slots of one digit go to consecutive addresses
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const int idx = i * RS_THREADS + threadIdx.x;
-        if (full || idx < tile_n) {
-            const W k = s_keys[idx];
-            const uint32_t d = digit(k);
-            const long long g = s_goff[d] + idx;
-            if (MULTI_OUT) s_outp[d][g] = k;
-            else out[g] = k;
-            if (HAS_VAL) vout[g] = s_vals[idx];
-        }
-    }
+    if (n - (uint64_t)tile * TILE >= (uint64_t)TILE)
+        radix_tile<W, DigitFn, MULTI_OUT, true>(in, out, n, digit, digit_base, status, pos_out, local_base, tile, s_keys, s_whist, s_goff64, s_goff32,
+                                                s_loff, s_outp, s_tmp);
+    else
+        radix_tile<W, DigitFn, MULTI_OUT, false>(in, out, n, digit, digit_base, status, pos_out, local_base, tile, s_keys, s_whist, s_goff64, s_goff32,
+                                                 s_loff, s_outp, s_tmp);
 }
 
 // per-destination counts for the router (<= 16 destinations): registers -> warp reduce -> atomics

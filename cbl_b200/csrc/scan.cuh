@@ -50,13 +50,15 @@ template <class T, int THREADS> __device__ __forceinline__ T block_excl_scan(T v
 // Decoupled look-back over 64-bit status words (2 flag bits + 62-bit value), executed by warp 0.
 // Tiles must be numbered by a ticket counter so every predecessor is already resident.
 // Returns the exclusive prefix of `agg` over all earlier tiles (same value in every lane of warp 0).
-__device__ __forceinline__ uint64_t lookback_warp(volatile uint64_t* status, uint32_t tile, uint64_t agg) {
+// Split form: lookback_publish (one thread, as early as possible: successors can then add this tile's aggregate
+// without waiting) and lookback_resolve (warp 0, as late as possible: everything that does not need the prefix can
+// be done in between, by all warps).
+__device__ __forceinline__ void lookback_publish(volatile uint64_t* status, uint32_t tile, uint64_t agg) {
+    status[tile] = (tile == 0 ? LB_FLAG_INCL : LB_FLAG_AGG) | agg;
+}
+__device__ __forceinline__ uint64_t lookback_resolve(volatile uint64_t* status, uint32_t tile, uint64_t agg) {
     const unsigned lane = lane_id();
-    if (tile == 0) {
-        if (lane == 0) status[0] = LB_FLAG_INCL | agg;
-        return 0;
-    }
-    if (lane == 0) status[tile] = LB_FLAG_AGG | agg;
+    if (tile == 0) return 0;
     uint64_t excl = 0;
     long long base = (long long)tile - 1;
     for (;;) {
@@ -79,6 +81,10 @@ __device__ __forceinline__ uint64_t lookback_warp(volatile uint64_t* status, uin
     }
     if (lane == 0) status[tile] = LB_FLAG_INCL | (excl + agg);
     return excl;
+}
+__device__ __forceinline__ uint64_t lookback_warp(volatile uint64_t* status, uint32_t tile, uint64_t agg) {
+    if (lane_id() == 0) lookback_publish(status, tile, agg);
+    return lookback_resolve(status, tile, agg);
 }
 
 // Ticket + look-back for a whole block: returns the tile id (via *tile_out) and the exclusive prefix.

@@ -155,6 +155,11 @@ int32_t cbl_sync(cbl_t* h);
 void* cbl_stream(const cbl_t* h);             /* the handle's cudaStream_t */
 uint64_t cbl_launch_count(void);              /* kernels launched by this library so far */
 const char* cbl_build_info(void);
+/* device memory: the library keeps the blocks it frees in a per-stream arena (no driver allocation in the steady
+ * state; the reference relies on the Rust global allocator the same way).  cbl_mem_trim returns every cached block
+ * of `device` to the driver (synchronises the device); cbl_mem_cached_bytes = bytes currently cached. */
+int32_t cbl_mem_trim(int32_t device);
+uint64_t cbl_mem_cached_bytes(void);
 /* per-kernel device time (CUDA events around every launch); off by default.  report: JSON text
  * {"kernel": {"n": launches, "ms": total}, ...}, clears the accumulated records */
 void cbl_profile_enable(int32_t on);
