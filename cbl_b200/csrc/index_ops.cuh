@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(OP_THREADS) probe_edits_kernel(
 // Bucket directory rebuild
 // ---------------------------------------------------------------------------------------------
 // (a) clear the bits of buckets that end up empty
-__global__ void clear_emptied_kernel(const uint32_t* __restrict__ bucket_prefix, const uint32_t* __restrict__ bucket_off,
+static __global__ void clear_emptied_kernel(const uint32_t* __restrict__ bucket_prefix, const uint32_t* __restrict__ bucket_off,
                                      const int* __restrict__ delta, uint32_t nb, uint2* __restrict__ new_dir) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
@@ -148,7 +148,7 @@ __global__ void clear_emptied_kernel(const uint32_t* __restrict__ bucket_prefix,
 
 // (b) rank directory: dir[i].y = number of set bits before word i; *nb_out = total set bits.
 // Single pass: per-thread popcounts, warp-shuffle scan, block scan, decoupled look-back across tiles.
-__global__ void __launch_bounds__(OP_THREADS) rank_directory_kernel(uint2* __restrict__ dir, uint64_t n_words, volatile uint64_t* status,
+static __global__ void __launch_bounds__(OP_THREADS) rank_directory_kernel(uint2* __restrict__ dir, uint64_t n_words, volatile uint64_t* status,
                                                                     uint32_t* tile_counter, unsigned long long* __restrict__ nb_out) {
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_excl;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(OP_THREADS) rank_directory_kernel(uint2* __res
 }
 
 // (c) surviving old buckets -> their new rank
-__global__ void fill_sizes_old_kernel(const uint32_t* __restrict__ bucket_prefix, const uint32_t* __restrict__ bucket_off,
+static __global__ void fill_sizes_old_kernel(const uint32_t* __restrict__ bucket_prefix, const uint32_t* __restrict__ bucket_off,
                                       const int* __restrict__ delta, uint32_t nb, const uint2* __restrict__ new_dir,
                                       uint32_t* __restrict__ size_new, uint32_t* __restrict__ prefix_new) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,7 +208,7 @@ __global__ void fill_sizes_ins_kernel(const W* __restrict__ ins_key, uint64_t ni
 }
 
 // (e) exclusive scan of u32 sizes -> u32 offsets (n entries in, n+1 out: out[n] = total)
-__global__ void __launch_bounds__(OP_THREADS) scan_sizes_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ out,
+static __global__ void __launch_bounds__(OP_THREADS) scan_sizes_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ out,
                                                                 uint2* __restrict__ range, volatile uint64_t* status,
                                                                 uint32_t* tile_counter) {
     __shared__ uint32_t s_tile;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256) build_sub_kernel(IndexView<Suf> ix, int s
 }
 
 // bucket sizes (prefix, size) — a by-product of the CSR offsets (src/wordset/mod.rs:258-263)
-__global__ void bucket_sizes_kernel(const uint32_t* __restrict__ bucket_off, uint32_t nb, uint32_t* __restrict__ sizes) {
+static __global__ void bucket_sizes_kernel(const uint32_t* __restrict__ bucket_off, uint32_t nb, uint32_t* __restrict__ sizes) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < nb) sizes[r] = bucket_off[r + 1] - bucket_off[r];
 }

@@ -1,0 +1,5 @@
+// Index<uint64_t, uint64_t>: see cbl_index_impl.cuh
+#include "cbl_index_impl.cuh"
+namespace cbl {
+CBL_INSTANTIATE_INDEX(make_index_u64_u64, uint64_t, uint64_t)
+}

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
 // Dense per-prefix counters -> directory.  One warp handles 32 directory words (1024 prefixes):
 // coalesced counter rows, ballots give the bit words, warp sums the element counts.
 // dir[w] = {bits, rank}; word_off[w] = number of elements in prefixes below 32 * w; totals[0] = nb, totals[1] = n.
-__global__ void __launch_bounds__(256) dir_bits_kernel(const uint32_t* __restrict__ prefix_cnt, uint64_t n_words, uint2* __restrict__ dir,
+static __global__ void __launch_bounds__(256) dir_bits_kernel(const uint32_t* __restrict__ prefix_cnt, uint64_t n_words, uint2* __restrict__ dir,
                                                        uint32_t* __restrict__ word_off, volatile uint64_t* status_rank,
                                                        volatile uint64_t* status_off, uint32_t* tile_counter,
                                                        unsigned long long* __restrict__ totals) {
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) dir_bits_kernel(const uint32_t* __restric
 }
 
 // bucket_prefix / bucket_off / bucket_range of every occupied prefix (thread = directory word)
-__global__ void dir_fill_kernel(const uint32_t* __restrict__ prefix_cnt, const uint2* __restrict__ dir, const uint32_t* __restrict__ word_off,
+static __global__ void dir_fill_kernel(const uint32_t* __restrict__ prefix_cnt, const uint2* __restrict__ dir, const uint32_t* __restrict__ word_off,
                                 uint64_t n_words, uint32_t* __restrict__ bucket_prefix, uint32_t* __restrict__ bucket_off,
                                 uint2* __restrict__ bucket_range, uint32_t nb, uint32_t n) {
     const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

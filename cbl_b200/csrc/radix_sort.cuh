@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(RH_THREADS) radix_hist_kernel(const W* __restr
 }
 
 // hist[pass][256] -> exclusive digit bases, in place (one block per pass)
-__global__ void __launch_bounds__(256) radix_scan_hist_kernel(unsigned long long* __restrict__ hist) {
+static __global__ void __launch_bounds__(256) radix_scan_hist_kernel(unsigned long long* __restrict__ hist) {
     __shared__ unsigned long long tmp[33];
     unsigned long long* h = hist + (size_t)blockIdx.x * 256;
     unsigned long long v = h[threadIdx.x], total;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) route_hist_kernel(const W* __restrict__ k
     }
 }
 
-__global__ void gather_u8_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ pos, uint64_t n, uint8_t* __restrict__ out) {
+static __global__ void gather_u8_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ pos, uint64_t n, uint8_t* __restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = src[pos[i]];
 }
