@@ -39,6 +39,7 @@ SIGNATURES = {
     "cbl_remove_seqs_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t]),
     "cbl_contains_seqs_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t, vp]),
     "cbl_count_kmers": (C.c_int32, [vp, u64p, C.c_size_t, u64p]),
+    "cbl_last_kmer_count": (C.c_int32, [vp, u64p]),
     "cbl_contains_kmers": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vp]),
     "cbl_insert_kmers": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vp]),
     "cbl_remove_kmers": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vp]),

@@ -169,13 +169,19 @@ class CBL:
         self._chk(self._L.cbl_count_kmers(self._h, offsets.ctypes.data_as(u64p), len(offsets) - 1, C.byref(v)))
         return int(v.value)
 
+    def last_kmer_count(self) -> int:
+        """Words / answers produced by the last sequence call (fewer than count_kmers after non-ACGT bytes, F8)."""
+        v = C.c_uint64()
+        self._chk(self._L.cbl_last_kmer_count(self._h, C.byref(v)))
+        return int(v.value)
+
     def contains_seqs(self, buf: np.ndarray, offsets: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = self.count_kmers(offsets)
         if out is None:
             out = np.zeros(max(n, 1), dtype=np.uint8)
         self._chk(self._L.cbl_contains_seqs(self._h, buf.ctypes.data, offsets.ctypes.data_as(u64p), len(offsets) - 1, out.ctypes.data))
-        return out[:n]
+        return out[: self.last_kmer_count()]
 
     # device-resident buffers: raw device pointers (e.g. torch_tensor.data_ptr())
     def insert_seqs_dev(self, d_buf: int, offsets: np.ndarray) -> None:
@@ -408,6 +414,7 @@ class CBL:
         hi = np.zeros(max(n, 1), dtype=np.uint64)
         self._chk(self._L.cbl_seq_words(self._h, buf.ctypes.data, offsets.ctypes.data_as(u64p), len(offsets) - 1,
                                         lo.ctypes.data_as(u64p), hi.ctypes.data_as(u64p), int(brute)))
+        n = self.last_kmer_count()
         return lo[:n], hi[:n]
 
     def sync(self) -> None:

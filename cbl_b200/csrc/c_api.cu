@@ -223,7 +223,7 @@ int32_t cbl_contains_seq(cbl_t* h, const uint8_t* seq, size_t len, uint8_t* out,
         need(h, "handle"); need(seq, "seq"); need(out, "out");
         uint64_t off[2] = {0, len};
         h->ix->contains_seqs(seq, off, 1, out);
-        if (n_out) *n_out = len - h->ix->config().k + 1;
+        if (n_out) *n_out = (size_t)h->ix->last_produced;   // len - K + 1, fewer after non-ACGT bytes (F8)
     });
 }
 int32_t cbl_contains_all(cbl_t* h, const uint8_t* seq, size_t len, int32_t* out) {
@@ -234,9 +234,13 @@ int32_t cbl_contains_all(cbl_t* h, const uint8_t* seq, size_t len, int32_t* out)
         std::vector<uint8_t> r(len - h->ix->config().k + 1);
         h->ix->contains_seqs(seq, off, 1, r.data());
         int all = 1;
-        for (uint8_t b : r) if (!b) { all = 0; break; }
+        for (uint64_t i = 0; i < h->ix->last_produced; i++) if (!r[i]) { all = 0; break; }
         *out = all;
     });
+}
+
+int32_t cbl_last_kmer_count(const cbl_t* h, uint64_t* out) {
+    return guard(mut(h), [&] { need(h, "handle"); need(out, "out"); *out = h->ix->last_produced; });
 }
 
 int32_t cbl_insert_seqs(cbl_t* h, const uint8_t* buf, const uint64_t* offsets, size_t n_seqs) {

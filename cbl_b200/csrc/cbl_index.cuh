@@ -67,6 +67,9 @@ public:
     virtual void load_sorted_words(const uint64_t* lo, const uint64_t* hi, uint64_t n) = 0;
     virtual void sync() = 0;
     std::string last_error;
+    // words / answers produced by the last sequence call: sum of (len - K + 1) over the records, or fewer when the
+    // reads held non-ACGT bytes and the reference's dropping behaviour was reproduced
+    uint64_t last_produced = 0;
 };
 
 IIndex* make_index(const Config& cfg);

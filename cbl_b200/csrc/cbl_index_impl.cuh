@@ -14,6 +14,7 @@
 #include "index_ops.cuh"
 #include "merge_ops.cuh"
 #include "radix_sort.cuh"
+#include "sanitize.cuh"
 #include "seq_words.cuh"
 
 namespace cbl {
@@ -263,18 +264,59 @@ public:
     }
     static void throw_bad_byte(unsigned long long e) {
         throw Error(CBL_EINVAL, "non-ACGT byte in sequence near byte offset " + std::to_string(e) +
-                                    " (the GPU path rejects what the reference silently drops; see DESIGN.md)");
+                                    " (not supported on this entry point: the fused multi-GPU route; see DESIGN.md)");
     }
-    // same, synchronous: throws EINVAL on a non-ACGT byte
-    void run_seq_words(const SeqBatch& b, int mode, bool brute, W* d_words, uint8_t* d_flags, cudaStream_t s) {
-        if (b.n_chunks == 0) return;
+    // Reads with non-nucleotide bytes (sanitize.cuh): every reference chunk of `in` becomes one clean
+    // single-chunk piece of K + b bytes that yields 1 + b words.  Returns the number of words the batch produces.
+    struct Sanitized {
+        DevBuf<uint8_t> clean;
+        DevPieces dp;
+        uint64_t n_kmers = 0;
+    };
+    void sanitize_batch(const SeqBatch& in, Sanitized& out, cudaStream_t s) {
+        const uint64_t nc = in.n_chunks;
+        DevBuf<uint32_t> counts(nc, s);
+        const unsigned grid = (unsigned)std::min<uint64_t>(nc, 1u << 30);
+        CBL_LAUNCH(sanitize_chunks_kernel, grid, SAN_THREADS, 0, s, in, cfg_.k, counts.get(), (const uint64_t*)nullptr, (uint8_t*)nullptr);
+        std::vector<uint32_t> b(nc);
+        CUDA_CHECK(cudaMemcpyAsync(b.data(), counts.get(), nc * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        PieceList pl;
+        pl.chunk0.push_back(0);
+        uint64_t bytes = 0;
+        for (uint64_t c = 0; c < nc; c++) {
+            pl.byte_off.push_back(bytes);
+            pl.out_off.push_back(pl.n_kmers);
+            pl.kmers.push_back(1 + b[c]);
+            pl.n_kmers += 1 + b[c];
+            pl.chunk0.push_back(c + 1);
+            bytes += (uint64_t)cfg_.k + b[c];
+        }
+        pl.n_chunks = nc;
+        out.clean.alloc(bytes + 64, s);
+        upload_pieces(pl, 0, nc, 0, out.clean.get(), bytes, out.dp, s);
+        CBL_LAUNCH(sanitize_chunks_kernel, grid, SAN_THREADS, 0, s, in, cfg_.k, (uint32_t*)nullptr, (const uint64_t*)out.dp.byte_off.get(), out.clean.get());
+        out.n_kmers = pl.n_kmers;
+    }
+    // Synchronous.  Returns the number of words / answers written (at the front of d_words / d_flags): the batch's
+    // k-mer count, or fewer when the reads held non-ACGT bytes and the reference's behaviour (F8) was reproduced.
+    uint64_t run_seq_words(const SeqBatch& b, uint64_t n_kmers, int mode, bool brute, W* d_words, uint8_t* d_flags, cudaStream_t s) {
+        if (b.n_chunks == 0) return 0;
         DevBuf<unsigned long long> err(1, s);
         CUDA_CHECK(cudaMemsetAsync(err.get(), 0xFF, 8, s));
         launch_seq_words(b, mode, brute, d_words, d_flags, err.get(), s);
         unsigned long long e = 0;
         CUDA_CHECK(cudaMemcpyAsync(&e, err.get(), 8, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
-        if (e != ULLONG_MAX) throw_bad_byte(e);
+        if (e == ULLONG_MAX) return n_kmers;
+        Sanitized sn;
+        sanitize_batch(b, sn, s);
+        CUDA_CHECK(cudaMemsetAsync(err.get(), 0xFF, 8, s));
+        launch_seq_words(sn.dp.batch, mode, brute, d_words, d_flags, err.get(), s);
+        CUDA_CHECK(cudaMemcpyAsync(&e, err.get(), 8, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (e != ULLONG_MAX) throw Error(CBL_ECUDA, "internal: sanitised reads still hold a non-ACGT byte");
+        return sn.n_kmers;
     }
 
     // ------------------------------------------------------------------------------------------
@@ -527,6 +569,7 @@ public:
         check_records(offsets, n_seqs);
         PieceList pl;
         build_pieces(offsets, 0, n_seqs, pl);
+        last_produced = 0;
         size_t p = 0;
         const size_t np = pl.kmers.size();
         while (p < np) {
@@ -539,9 +582,10 @@ public:
             tr.mark("upload pieces");
             DevBuf<W> a(nk, st_), b(nk, st_);
             tr.mark("alloc a,b");
-            run_seq_words(dp.batch, 0, false, a.get(), nullptr, st_);
+            const uint64_t produced = run_seq_words(dp.batch, nk, 0, false, a.get(), nullptr, st_);
+            last_produced += produced;
             tr.mark("seq_words (sync inside)");
-            mutate_with_words(a.get(), b.get(), nk, mode);
+            mutate_with_words(a.get(), b.get(), produced, mode);
             tr.mark("mutate_with_words", true);
             p = q;
         }
@@ -558,21 +602,23 @@ public:
         check_records(offsets, n_seqs);
         PieceList pl;
         build_pieces(offsets, 0, n_seqs, pl);
+        last_produced = 0;
         if (pl.kmers.empty()) return;
         ensure_sub();
         DevPieces dp;
         upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, st_);
-        run_seq_words(dp.batch, 1, false, nullptr, d_out, st_);
+        last_produced = run_seq_words(dp.batch, pl.n_kmers, 1, false, nullptr, d_out, st_);
     }
     void seq_words_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, void* d_words, bool brute) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         check_records(offsets, n_seqs);
         PieceList pl;
         build_pieces(offsets, 0, n_seqs, pl);
+        last_produced = 0;
         if (pl.kmers.empty()) return;
         DevPieces dp;
         upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, st_);
-        run_seq_words(dp.batch, 0, brute, (W*)d_words, nullptr, st_);
+        last_produced = run_seq_words(dp.batch, pl.n_kmers, 0, brute, (W*)d_words, nullptr, st_);
     }
 
     // host buffers: records are grouped (~CBL_GROUP_BYTES each) and streamed through the device
@@ -716,7 +762,30 @@ public:
             CUDA_CHECK(cudaMemcpyAsync(&errs[i], slots[i].err.get(), 8, cudaMemcpyDeviceToHost, slots[i].s));
         }
         for (int i = 0; i < n_slots; i++) CUDA_CHECK(cudaStreamSynchronize(slots[i].s));
-        for (int i = 0; i < n_slots; i++) if (errs[i] != ULLONG_MAX) throw_bad_byte(errs[i]);
+        last_produced = pl.n_kmers;
+        bool bad = false;
+        for (int i = 0; i < n_slots; i++) bad = bad || errs[i] != ULLONG_MAX;
+        if (bad) contains_seqs_unpipelined(seq, offsets, n_seqs, out);   // non-ACGT bytes: the reference's behaviour (F8), slow path
+    }
+    // group after group through the device path; answers are compacted in reference order (record after record,
+    // chunk after chunk), last_produced = how many there are
+    void contains_seqs_unpipelined(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint8_t* out) {
+        uint64_t total = 0;
+        for_each_group(offsets, n_seqs, [&](size_t r, size_t q) {
+            const uint64_t b0 = offsets[r], nbytes = offsets[q] - b0;
+            DevBuf<uint8_t> d(nbytes + 64, st_);
+            CUDA_CHECK(cudaMemcpyAsync(d.get(), seq + b0, nbytes, cudaMemcpyHostToDevice, st_));
+            std::vector<uint64_t> off(q - r + 1);
+            uint64_t nk = 0;
+            for (size_t i = r; i <= q; i++) off[i - r] = offsets[i] - b0;
+            for (size_t i = r; i < q; i++) nk += offsets[i + 1] - offsets[i] - (uint64_t)cfg_.k + 1;
+            DevBuf<uint8_t> flags(nk, st_);
+            contains_seqs_dev(d.get(), nbytes, off.data(), q - r, flags.get());
+            if (last_produced) CUDA_CHECK(cudaMemcpyAsync(out + total, flags.get(), last_produced, cudaMemcpyDeviceToHost, st_));
+            CUDA_CHECK(cudaStreamSynchronize(st_));
+            total += last_produced;
+        });
+        last_produced = total;
     }
     void seq_words(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint64_t* lo, uint64_t* hi, bool brute) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
@@ -730,7 +799,7 @@ public:
         CUDA_CHECK(cudaMemcpyAsync(d.get(), seq + offsets[0], nbytes, cudaMemcpyHostToDevice, st_));
         DevBuf<W> w(nk, st_);
         seq_words_dev(d.get(), nbytes, off.data(), n_seqs, w.get(), brute);
-        download_words(w.get(), nk, lo, hi);
+        download_words(w.get(), last_produced, lo, hi);
     }
     void download_words(const W* d, uint64_t n, uint64_t* lo, uint64_t* hi) {
         if (n == 0) return;

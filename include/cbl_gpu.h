@@ -71,6 +71,12 @@ int32_t cbl_remove_seqs_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offs
 int32_t cbl_contains_seqs_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, uint8_t* d_out);
 /* number of k-mers (= answers) the records yield */
 int32_t cbl_count_kmers(const cbl_t* h, const uint64_t* offsets, size_t n_seqs, uint64_t* out);
+/* Non-ACGT bytes: like the reference (filter_map in src/kmer.rs:133-135 and src/cbl.rs:262,282 while chunking is
+ * on raw byte offsets, src/cbl.rs:239-243) every 2048-k-mer chunk drops them: its first k-mer is built from the
+ * valid bytes among its first K bytes and every later valid byte yields one more word.  Such input takes a slower
+ * path; words / answers come out compacted, in the reference's order, at the front of the output buffer.
+ * cbl_last_kmer_count = how many the handle's last sequence call produced (= cbl_count_kmers for clean reads). */
+int32_t cbl_last_kmer_count(const cbl_t* h, uint64_t* out);
 
 /* ---- single k-mers: contains / insert / remove (src/cbl.rs:219-235), batched.  k-mers are IntKmer
  *      integers (first base most significant, A=0 C=1 T=2 G=3).  out[i] (may be NULL) = whether

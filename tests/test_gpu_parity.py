@@ -300,8 +300,6 @@ def test_errors(gpu):
         g.insert_seq(b"ACGT")
     with pytest.raises(gpu.CBLError, match="smaller than K"):
         g.contains_seq(b"ACGT")
-    with pytest.raises(gpu.CBLError, match="non-ACGT"):
-        g.insert_seq(b"ACGT" * 10 + b"N" + b"ACGT" * 10)
     assert g.count() == 0  # a rejected call leaves the set untouched
     c = gpu.CBL.new_canonical(25, 64, 24)
     with pytest.raises(gpu.CBLError, match="One of the index is canonical while the other isn't"):
@@ -372,3 +370,70 @@ def test_route_and_gather(gpu, k, tb, pb):
         assert torch.equal(eng.gather(flags, pos), flags[pos.long()])
         if world > 1:
             assert counts.min() > 0.8 * counts.max()  # equal-mass splitters balance random DNA
+
+
+# ------------------------------------------------------------------------------------------------
+# non-ACGT bytes are dropped by filter_map while chunking stays on raw byte offsets
+# (src/kmer.rs:133-135, src/cbl.rs:239-289) — reproduced on the GPU by the sanitising slow path
+# ------------------------------------------------------------------------------------------------
+def with_junk(n, seed, every, junk=b"NnRY-*\n"):
+    """random DNA with a non-nucleotide byte roughly every `every` positions (plus the odd run of them)"""
+    rng = np.random.default_rng(seed)
+    s = util.random_dna(n, seed).copy()
+    idx = rng.integers(0, n, size=max(1, n // every))
+    s[idx] = np.frombuffer(junk, dtype=np.uint8)[rng.integers(0, len(junk), size=len(idx))]
+    if n > 400:
+        s[300:340] = ord("N")   # a run longer than K=25: a chunk whose first K bytes hold few valid bases
+    return s.tobytes()
+
+
+@pytest.mark.parametrize("k,tb,pb", [(7, 32, 14), (25, 64, 24), (31, 128, 24), (59, 128, 28)])
+@pytest.mark.parametrize("canonical", [False, True])
+def test_non_acgt_words_match_reference_behaviour(gpu, orc, k, tb, pb, canonical):
+    g = gpu.CBL(k, tb, pb, canonical)
+    o = orc.OracleCBL(k, tb, pb, canonical)
+    recs = [with_junk(n, seed=40 + i, every=e) for i, (n, e) in enumerate([(k, 3), (k + 5, 4), (500, 50), (2048 + k - 1, 100), (2048 + k, 7),
+                                                                           (4096 + k + 3, 300), (10000, 2000), (70001, 500)])]
+    recs.append(b"N" * (k + 40))                       # nothing valid at all: one all-A word per chunk
+    recs.append(b"N" * k + b"ACGT" * 20)               # empty first k-mer
+    recs.append(util.random_dna(5000, 3).tobytes())    # a clean record inside a dirty batch
+    for r in recs:                                      # one record per call
+        exp = ints(*o.seq_words(r))
+        lo, hi = g.seq_words([r])
+        assert_same(ints(lo, hi), exp, f"F8 seq_words len={len(r)}")
+        assert g.last_kmer_count() == len(exp)
+    expect = []
+    for r in recs:
+        expect += ints(*o.seq_words(r))
+    lo, hi = g.seq_words(recs)                          # the whole batch in one call
+    assert_same(ints(lo, hi), expect, "F8 seq_words, batch")
+
+
+@pytest.mark.parametrize("canonical", [False, True])
+def test_non_acgt_insert_contains_remove(gpu, orc, canonical):
+    k, tb, pb = 25, 64, 24
+    g = gpu.CBL(k, tb, pb, canonical)
+    o = orc.OracleCBL(k, tb, pb, canonical)
+    a = with_junk(60000, seed=5, every=400)
+    b = with_junk(30000, seed=6, every=150)
+    clean = util.random_dna(20000, 9).tobytes()
+    for r in (a, clean):
+        g.insert_seq(r)
+        o.insert_seq(r)
+    assert g.count() == o.count()
+    assert_same(g.words(), ints(*o.iter_words()), "set after inserting reads with N")
+    for q in (a, b, a[100:9000] + b[:5000], clean):
+        got = g.contains_seq(q)
+        exp = o.contains_seq(q)
+        assert len(got) == len(exp) and np.array_equal(got.astype(np.uint8), exp), "F8 contains_seq"
+        assert g.contains_all(q) == bool(o.contains_all(q))
+    assert g.contains_all(a)
+    # batch entry points: answers compacted in reference order
+    buf, offs = gpu.concat_records([a, clean, b])
+    got = g.contains_seqs(buf, offs)
+    exp = np.concatenate([o.contains_seq(r) for r in (a, clean, b)])
+    assert np.array_equal(got, exp)
+    g.remove_seq(a)
+    o.remove_seq(a)
+    assert g.count() == o.count()
+    assert_same(g.words(), ints(*o.iter_words()), "set after removing reads with N")

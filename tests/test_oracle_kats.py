@@ -381,3 +381,25 @@ def test_serde_roundtrip(oracle_lib):
         assert d.serialize() == blob
     with pytest.raises(pyoracle.OracleError):
         c.deserialize(blob + b"\0")
+
+
+def test_non_acgt_equals_padded_clean_chunks(oracle_lib):
+    """The equivalence the GPU slow path (cbl_b200/csrc/sanitize.cuh) is built on: a chunk with non-ACGT bytes
+    yields the words of the clean string 'A'*(K-a) ++ valid(first K bytes) ++ valid(rest)."""
+    valid = set(b"ACGTacgt")
+    for k, tb, pb, canonical in [(7, 32, 14, False), (25, 64, 24, True), (31, 128, 24, False), (59, 128, 28, True)]:
+        c = OracleCBL(k, tb, pb, canonical=canonical, lib=oracle_lib)
+        rng = np.random.default_rng(k)
+        s = util.random_dna(9000, seed=k).copy()
+        s[rng.integers(0, len(s), size=120)] = ord("N")
+        s[2040:2040 + k + 3] = ord("n")
+        seq = s.tobytes()
+        expect = util.to_int_list(*c.seq_words(seq))
+        got = []
+        for start in range(0, len(seq) - k + 1, 2048):
+            chunk = seq[start:min(start + 2048 + k - 1, len(seq))]
+            head = bytes(ch for ch in chunk[:k] if ch in valid)
+            rest = bytes(ch for ch in chunk[k:] if ch in valid)
+            clean = b"A" * (k - len(head)) + head + rest
+            got += util.to_int_list(*c.seq_words(clean))
+        assert got == expect
