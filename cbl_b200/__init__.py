@@ -5,8 +5,8 @@ The product is the CUDA library ``cbl_b200/csrc/libcbl_gpu.so`` behind the C ABI
 There is no CPU fallback: importing fails if the CUDA library has not been built.
 """
 from ._lib import LIB_PATH, lib
-from .cbl import CBL, CBLError, OP_AND, OP_OR, OP_SUB, OP_XOR, concat_records, launch_count, profile_enable, profile_report
+from .cbl import CBL, CBLError, OP_AND, OP_OR, OP_SUB, OP_XOR, concat_records, launch_count, profile_enable, profile_report, sort_fallback_count
 
 lib()  # fail loudly at import time if the native library is missing
 
-__all__ = ["CBL", "CBLError", "concat_records", "launch_count", "profile_enable", "profile_report", "lib", "LIB_PATH", "OP_OR", "OP_AND", "OP_SUB", "OP_XOR"]
+__all__ = ["CBL", "CBLError", "concat_records", "launch_count", "sort_fallback_count", "profile_enable", "profile_report", "lib", "LIB_PATH", "OP_OR", "OP_AND", "OP_SUB", "OP_XOR"]

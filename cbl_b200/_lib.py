@@ -74,6 +74,7 @@ SIGNATURES = {
     "cbl_sync": (C.c_int32, [vp]),
     "cbl_stream": (vp, [vp]),
     "cbl_launch_count": (C.c_uint64, []),
+    "cbl_sort_fallback_count": (C.c_uint64, []),
     "cbl_build_info": (C.c_char_p, []),
     "cbl_mem_trim": (C.c_int32, [C.c_int32]),
     "cbl_mem_cached_bytes": (C.c_uint64, []),

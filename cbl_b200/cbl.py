@@ -429,6 +429,11 @@ def launch_count() -> int:
     return int(_lib.lib().cbl_launch_count())
 
 
+def sort_fallback_count() -> int:
+    """Batches the segment sort handed back to the plain LSD radix passes (heavily repeated words only)."""
+    return int(_lib.lib().cbl_sort_fallback_count())
+
+
 def profile_enable(on: bool) -> None:
     _lib.lib().cbl_profile_enable(int(on))
 

@@ -490,6 +490,7 @@ int32_t cbl_seq_words(cbl_t* h, const uint8_t* buf, const uint64_t* offsets, siz
 int32_t cbl_sync(cbl_t* h) { return guard(h, [&] { need(h, "handle"); h->ix->sync(); }); }
 void* cbl_stream(const cbl_t* h) { return h ? (void*)h->ix->stream() : nullptr; }
 uint64_t cbl_launch_count(void) { return g_launches.load(); }
+uint64_t cbl_sort_fallback_count(void) { return g_sort_fallbacks.load(); }
 void cbl_profile_enable(int32_t on) { g_prof_on.store(on ? 1 : 0); }
 int32_t cbl_profile_report(char* out, size_t cap) {
     return guard(nullptr, [&] {

@@ -15,6 +15,7 @@
 namespace cbl {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_sort_fallbacks{0};
 std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;

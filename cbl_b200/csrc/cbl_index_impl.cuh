@@ -14,6 +14,7 @@
 #include "index_ops.cuh"
 #include "merge_ops.cuh"
 #include "radix_sort.cuh"
+#include "seg_sort.cuh"
 #include "sanitize.cuh"
 #include "seq_words.cuh"
 
@@ -108,11 +109,21 @@ public:
         if (batch_kmers_ > RS_MAX_KEYS) batch_kmers_ = RS_MAX_KEYS;
         if (batch_kmers_ < CHUNK_KMERS) batch_kmers_ = CHUNK_KMERS;
         if (uint64_t g = env_u64("CBL_L2_FETCH", 0)) CUDA_CHECK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
+        // L2::evict_last lines live in the persisting set-aside; without one the hint is a no-op
+        if (uint64_t mb = env_u64("CBL_L2_PERSIST_MB", 0)) {
+            int max_persist = 0;
+            CUDA_CHECK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg.device));
+            CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)mb << 20, (size_t)max_persist)));
+        }
         static bool attr_done = false;
         if (!attr_done) {
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, ByteDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, ByteDigit<W>>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CUDA_CHECK(cudaFuncSetAttribute((seg_sort_kernel<W, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SsTile<W>::SMEM));
+            CUDA_CHECK(cudaFuncSetAttribute((seg_sort_kernel<W, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CUDA_CHECK(cudaFuncSetAttribute((seg_sort_kernel<W, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SsTile<W>::SMEM));
+            CUDA_CHECK(cudaFuncSetAttribute((seg_sort_kernel<W, false>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_OR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_AND>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_SUB>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -323,15 +334,49 @@ public:
     // sort / unique
     // ------------------------------------------------------------------------------------------
     // sorts n keys; returns the buffer (a or b) that holds the result
+    // Hybrid (default): LSD passes over the top digits only, then the in-shared-memory segment sort (seg_sort.cuh).
+    // The number of passes is chosen so that the largest group of words sharing their sorted top bits fits a segment
+    // tile: for k-mer data the most frequent b-bit head of a necklace word has mass ~ 2K / 2^b.  Any other
+    // distribution is still sorted exactly: a segment that does not fit raises the fail flag and the batch is re-sorted
+    // by the plain LSD passes.  CBL_SORT=lsd selects the plain passes outright.
     W* sort_keys(W* a, W* b, uint64_t n) {
         if (n <= 1) return a;
         if (n > RS_MAX_KEYS) throw Error(CBL_EINVAL, "internal: sort batch too large");
         const int key_bits = P_.bits + P_.pos_bits;
-        const int n_pass = (key_bits + 7) / 8;
+        const int n_digits = (key_bits + 7) / 8;
+        int n_pass = n_digits;
+        const char* sort_env = getenv("CBL_SORT");
+        const bool hybrid = !(sort_env && std::string(sort_env) == "lsd");
+        if (hybrid) {
+            for (int c = 1; c < n_digits - 1; c++) {   // c LSD passes leave 8 * (n_digits - c) low bits to the segment sort
+                const int b = key_bits - 8 * (n_digits - c);
+                const double est = (double)n * (double)P_.bits / std::ldexp(1.0, b);
+                if (est * 1.5 <= (double)SsTile<W>::T) { n_pass = c; break; }
+            }
+        }
+        W* res = lsd_passes(a, b, n, n_digits - n_pass, n_pass);
+        if (n_pass == n_digits) return res;
+        W* other = res == a ? b : a;
+        DevBuf<unsigned> fail(1, st_);
+        fail.zero();
+        const int shift = 8 * (n_digits - n_pass);
+        if (shift <= 32)
+            CBL_LAUNCH((seg_sort_kernel<W, true>), (unsigned)div_up(n, SsTile<W>::T), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, fail.get());
+        else
+            CBL_LAUNCH((seg_sort_kernel<W, false>), (unsigned)div_up(n, SsTile<W>::T), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, fail.get());
+        unsigned h_fail = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&h_fail, fail.get(), sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        if (!h_fail) return other;
+        g_sort_fallbacks.fetch_add(1, std::memory_order_relaxed);
+        return lsd_passes(res, other, n, 0, n_digits);   // `res` still holds every word (grouped by its top digits)
+    }
+    // LSD passes over digits [first, first + n_pass); returns the buffer that holds the result
+    W* lsd_passes(W* a, W* b, uint64_t n, int first, int n_pass) {
         DevBuf<unsigned long long> hist((size_t)n_pass * 256, st_);
         hist.zero();
         unsigned hgrid = (unsigned)std::min<uint64_t>(div_up(n, RH_THREADS * RH_KEYS), 148 * 4);
-        CBL_LAUNCH((radix_hist_kernel<W>), hgrid, RH_THREADS, (size_t)n_pass * 256 * sizeof(uint32_t), st_, a, n, n_pass, hist.get());
+        CBL_LAUNCH((radix_hist_kernel<W>), hgrid, RH_THREADS, (size_t)n_pass * 256 * sizeof(uint32_t), st_, a, n, n_pass, hist.get(), first);
         CBL_LAUNCH(radix_scan_hist_kernel, n_pass, 256, 0, st_, hist.get());
         const uint64_t tiles = div_up(n, RsTile<W>::TILE);
         DevBuf<uint32_t> status(tiles * 256, st_), counter(1, st_);
@@ -341,7 +386,7 @@ public:
             status.zero();
             counter.zero();
             CBL_LAUNCH((radix_pass_kernel<W, false, ByteDigit<W>>), (unsigned)tiles, RS_THREADS, smem, st_, src, dst, nullptr, nullptr, n,
-                       ByteDigit<W>{8 * p}, hist.get() + (size_t)p * 256, status.get(), counter.get(), (uint32_t*)nullptr);
+                       ByteDigit<W>{8 * (first + p)}, hist.get() + (size_t)p * 256, status.get(), counter.get(), (uint32_t*)nullptr);
             std::swap(src, dst);
         }
         return src;

@@ -30,6 +30,7 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 #define CUDA_CHECK(x) ::cbl::cuda_check((x), #x, __FILE__, __LINE__)
 
 extern std::atomic<uint64_t> g_launches;  // every kernel launched by this library
+extern std::atomic<uint64_t> g_sort_fallbacks;  // batches the segment sort handed back to the plain LSD passes
 
 // Optional per-kernel device timing (CUDA events on the launching stream), off by default.
 // bench.py turns it on for a separate, untimed pass to attribute time to kernels.

@@ -99,12 +99,56 @@ template <class W> CBL_HD void necklace_brute(W w, int bits, W& neck, int& pos) 
     pos = bp;
 }
 
-// Exact fast path.  The minimal rotation starts with the longest circular run of zero bits, so only
+#ifndef CBL_NECKLACE_ALGO
+#define CBL_NECKLACE_ALGO 1
+#endif
+// Exact fast path, variant 1 (default): lexicographic elimination.  Bit i of `cand` stands for the rotation that
+// brings bit i of w to the top (p = bits-1-i); its k-th bit from the top is bit i of rotl(w, k).  Step k keeps the
+// candidates whose k-th bit is 0 if there are any (otherwise all of them have a 1 there and all stay), so after
+// step k the survivors are exactly the rotations with the smallest (k+1)-bit head.  The loop ends when one candidate
+// is left or bits steps are done (the survivors are then equal rotations of a periodic word and the highest bit =
+// smallest p wins, src/necklace/mod.rs:17-23).  The zero-run search of variant 0 is the first phase of the same
+// process; the tie-break between equally long runs costs one shift+mask per step instead of a rotate+compare per
+// candidate.  Steps are taken two at a time (an extra step on a single survivor changes nothing).
+template <class W> CBL_HD void necklace_elim(W w, int bits, W& neck, int& pos) {
+    const W mask = low_mask<W>(bits);
+    W cand = (W)(~w & mask);
+    if (cand == 0 || w == 0) { neck = w; pos = 0; return; }  // all ones / all zeros: every rotation equal
+    W wk = w;
+    for (int k = 1; k < bits && (cand & (W)(cand - 1)) != 0; k += 2) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < 2; u++) {
+            wk = (W)(((wk << 1) & mask) | (wk >> (bits - 1)));
+            const W n = (W)(cand & ~wk);
+            if (n != 0) cand = n;
+        }
+    }
+    const int p = bits - 1 - top_bit(cand);
+    neck = rotl_ring<W>(w, p, bits, mask);
+    pos = p;
+}
+
+template <class W> CBL_HD void necklace_runs(W w, int bits, W& neck, int& pos);
+// 64-bit words take the elimination loop; 128-bit words keep variant 0: the elimination loop compiled for u128 gives
+// wrong words on sm_100a with nvcc 12.9 (GPU parity tests, 2K = 118) although the same source is right on the host —
+// the same class of miscompile as the incremental rotation noted at necklace_brute.
+template <class W> CBL_HD void necklace_fast(W w, int bits, W& neck, int& pos) {
+#if CBL_NECKLACE_ALGO == 1
+    if (sizeof(W) == 8) necklace_elim<W>(w, bits, neck, pos);
+    else necklace_runs<W>(w, bits, neck, pos);
+#else
+    necklace_runs<W>(w, bits, neck, pos);
+#endif
+}
+
+// Exact fast path, variant 0 (CBL_NECKLACE_ALGO=0, kept for A/B runs).  The minimal rotation starts with the longest circular run of zero bits, so only
 // the starts of maximal-length zero runs are candidates.  y_k has bit i set iff bits i, i-1, .., i-k+1
 // (circularly) are all zero; y_{k+1} = z & rotl1(y_k).  The last non-empty y marks the candidates.
 // Candidates are visited by ascending rotation amount and replaced only on strict '<', which keeps
 // the reference's tie rule (smallest pos; src/necklace/mod.rs:17-23, pinned by :83-98).
-template <class W> CBL_HD void necklace_fast(W w, int bits, W& neck, int& pos) {
+template <class W> CBL_HD void necklace_runs(W w, int bits, W& neck, int& pos) {
     const W mask = low_mask<W>(bits);
     const W z = (W)(~w & mask);
     if (z == 0 || w == 0) { neck = w; pos = 0; return; }  // all ones / all zeros: every rotation equal

@@ -60,7 +60,8 @@ constexpr int RH_THREADS = 512;
 constexpr int RH_KEYS = 4;  // keys per thread per round
 template <class W>
 __global__ void __launch_bounds__(RH_THREADS) radix_hist_kernel(const W* __restrict__ keys, uint64_t n, int n_pass,
-                                                                unsigned long long* __restrict__ hist) {
+                                                                unsigned long long* __restrict__ hist, int first = 0) {
+    // rows of hist: digits first, first + 1, .., first + n_pass - 1 of the key (digit d = bits [8d, 8d + 8))
     extern __shared__ uint32_t sh_hist[];  // [n_pass][256]
     for (int i = threadIdx.x; i < n_pass * 256; i += RH_THREADS) sh_hist[i] = 0;
     __syncthreads();
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(RH_THREADS) radix_hist_kernel(const W* __restr
         for (int j = 0; j < RH_KEYS; j++) {
             const uint64_t i = base + (uint64_t)j * RH_THREADS + threadIdx.x;
             ok[j] = i < n;
-            k[j] = ok[j] ? keys[i] : (W)0;
+            k[j] = ok[j] ? (W)(keys[i] >> (8 * first)) : (W)0;
         }
 #pragma unroll
         for (int j = 0; j < RH_KEYS; j++) {

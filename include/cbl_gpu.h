@@ -160,6 +160,9 @@ int32_t cbl_seq_words(cbl_t* h, const uint8_t* buf, const uint64_t* offsets, siz
 int32_t cbl_sync(cbl_t* h);
 void* cbl_stream(const cbl_t* h);             /* the handle's cudaStream_t */
 uint64_t cbl_launch_count(void);              /* kernels launched by this library so far */
+/* batches whose segment sort (seg_sort.cuh) met a group of words too long for its tile and were re-sorted by the plain
+ * LSD passes: 0 for k-mer data, > 0 only for heavily repeated words (results are identical either way) */
+uint64_t cbl_sort_fallback_count(void);
 const char* cbl_build_info(void);
 /* device memory: the library keeps the blocks it frees in a per-stream arena (no driver allocation in the steady
  * state; the reference relies on the Rust global allocator the same way).  cbl_mem_trim returns every cached block

@@ -38,6 +38,7 @@ template <class W> static long check_bits(int bits, long n, std::mt19937_64& g) 
         int p1, p2;
         cbl::necklace_brute<W>(w, bits, n1, p1);
         cbl::necklace_fast<W>(w, bits, n2, p2);
+        { W n3; int p3; cbl::necklace_runs<W>(w, bits, n3, p3); if (n3 != n1 || p3 != p1) { n2 = ~n1; } }
         auto ref = orc::necklace_pos<u128>((u128)w, bits);
         if (n1 != n2 || p1 != p2 || (u128)n1 != ref.first || (size_t)p1 != ref.second) {
             if (bad < 5) fprintf(stderr, "necklace mismatch bits=%d w=%llx%016llx brute=(..,%d) fast=(..,%d) ref=(..,%zu)\n", bits,

@@ -437,3 +437,45 @@ def test_non_acgt_insert_contains_remove(gpu, orc, canonical):
     o.remove_seq(a)
     assert g.count() == o.count()
     assert_same(g.words(), ints(*o.iter_words()), "set after removing reads with N")
+
+
+# ------------------------------------------------------------------------------------------------
+# k3 + k3b: hybrid batch sort (LSD passes on the top digits + segment sort) == plain LSD sort, on inputs that
+# stress the segment sort: random reads, every k-mer repeated a few times (ties inside the bins), every k-mer
+# repeated thousands of times (segments longer than a tile -> fallback to the LSD passes), mostly-A reads
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,tb,pb", [(25, 64, 24), (31, 128, 24), (59, 128, 28), (7, 32, 14)])
+def test_hybrid_sort_equals_lsd_sort(gpu, orc, k, tb, pb, monkeypatch):
+    rng = np.random.default_rng(77)
+    block = util.random_dna(6000, 71)
+    inputs = {
+        "random": util.random_dna(1_500_000, 70),
+        "repeat x6": np.tile(block, 6),
+        "repeat x5000": np.tile(util.random_dna(400, 72), 5000),
+        "mostly A": low_complexity(600_000, 73),
+        "tiny": util.random_dna(k + 30, 74),
+    }
+    for name, seq in inputs.items():
+        monkeypatch.setenv("CBL_SORT", "lsd")
+        a = gpu.CBL(k, tb, pb)
+        a.insert_seq(seq)
+        monkeypatch.delenv("CBL_SORT")
+        before = gpu.sort_fallback_count()
+        b = gpu.CBL(k, tb, pb)
+        b.insert_seq(seq)
+        fell_back = gpu.sort_fallback_count() - before
+        la, ha = a.words_arrays()
+        lb, hb = b.words_arrays()
+        assert a.count() == b.count() and np.array_equal(la, lb) and np.array_equal(ha, hb), name
+        assert b.contains_seq(seq).all(), name
+        if name == "random" and k >= 25:
+            assert fell_back == 0, "random reads must not need the fallback"
+        if name == "repeat x5000" and k >= 25:
+            assert fell_back > 0, "a k-mer repeated 5000 times cannot fit a segment tile"
+        if name in ("repeat x6", "tiny"):
+            o = orc.OracleCBL(k, tb, pb)
+            o.insert_seq(seq)
+            assert_same(b.words(), ints(*o.iter_words()), name)
+        b.remove_seq(seq)
+        assert b.is_empty(), name
+    del rng
