@@ -276,19 +276,29 @@ __device__ __forceinline__ int eval_window(const Suf (&e)[Window<Suf, WB>::N], u
         for (int i = 0; i < WN; i++) eq |= e[i] == s;
         return eq ? 1 : 0;
     }
-    const uint32_t v0 = max(L, base), v1 = min(R, base + WN);  // valid slots of the window
-    uint32_t n_lt = 0;
-    bool eq = false;
+    // Window sticking out of the open range (first / last window of a bucket, or a range already narrowed): slots
+    // [lo, hi) of it are valid and ascending.  p(i) = "slot i is below the range, or valid and < s" is monotone over the
+    // window, so its first false slot is found by a branch-free bisection that drags the candidate element along
+    // (log2(WN) + 1 compares instead of one masked compare pair per slot).
+    const uint32_t lo = L > base ? L - base : 0u, hi = min(R - base, (uint32_t)WN);   // 0 <= lo < hi <= WN
+    Suf x[WN];
 #pragma unroll
-    for (int i = 0; i < WN; i++) {
-        const uint32_t idx = base + i;
-        const bool ok = idx >= v0 && idx < v1;
-        n_lt += ok && e[i] < s;
-        eq |= ok && e[i] == s;
+    for (int i = 0; i < WN; i++) x[i] = e[i];
+    uint32_t pos = 0;
+#pragma unroll
+    for (int half = WN / 2; half >= 1; half >>= 1) {
+        const uint32_t i = pos + (uint32_t)half - 1u;
+        const bool p = i < lo || (i < hi && x[half - 1] < s);
+#pragma unroll
+        for (int j = 0; j < half; j++) x[j] = p ? x[j + half] : x[j];
+        pos += p ? (uint32_t)half : 0u;
     }
-    if (eq) return 1;
-    if (n_lt == 0) { R = v0; if (R <= L) return 0; g = R - 1; return -1; }
-    if (n_lt == v1 - v0) { L = v1; if (R <= L) return 0; g = L; return -1; }
+    const Suf z = x[0];                                        // = e[pos]
+    const bool pz = pos < lo || (pos < hi && z < s);
+    const uint32_t n_lt = pos + (pz ? 1u : 0u);                // slots of the window that are "< s" (those below the range included)
+    if (!pz && pos < hi && z == s) return 1;
+    if (n_lt == lo) { R = base + lo; if (R <= L) return 0; g = R - 1; return -1; }   // every valid slot is > s
+    if (n_lt == hi) { L = base + hi; if (R <= L) return 0; g = L; return -1; }       // every valid slot is < s
     return 0;
 }
 
