@@ -15,6 +15,9 @@
 #include "merge_ops.cuh"
 #include "radix_sort.cuh"
 #include "seg_sort.cuh"
+#ifndef CBL_PROBE_WB
+#define CBL_PROBE_WB 32   // bytes per suffix window of the membership probe
+#endif
 #include "sanitize.cuh"
 #include "seq_words.cuh"
 
@@ -259,7 +262,7 @@ public:
             if (brute) CBL_LAUNCH((seq_words_kernel<W, Suf, 0, true, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
             else CBL_LAUNCH((seq_words_kernel<W, Suf, 0, false, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
         } else {
-            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
+            CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, CBL_PROBE_WB, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
         }
     }
     // membership of n words (MODE 3 of the fused kernel: same staged probe + deferred queue, no sequence front end);
@@ -270,7 +273,7 @@ public:
         sa.in_words = d_words;
         sa.n_in = n;
         const unsigned grid = (unsigned)std::min<uint64_t>(div_up(n, CHUNK_KMERS), 1u << 30);
-        CBL_LAUNCH((seq_words_kernel<W, Suf, 3, false, 32, 1>), grid, SW_THREADS, 0, s, SeqBatch{}, P_, (W*)nullptr, d_flags, view(),
+        CBL_LAUNCH((seq_words_kernel<W, Suf, 3, false, CBL_PROBE_WB, 1>), grid, SW_THREADS, 0, s, SeqBatch{}, P_, (W*)nullptr, d_flags, view(),
                    (unsigned long long*)nullptr, sa);
     }
     static void throw_bad_byte(unsigned long long e) {
@@ -1034,7 +1037,7 @@ public:
     void gather_u8_dev(const uint8_t* d_src, const uint32_t* d_pos, uint64_t n, uint8_t* d_out) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         if (n == 0) return;
-        CBL_LAUNCH(gather_u8_kernel, (unsigned)div_up(n, 256), 256, 0, st_, d_src, d_pos, n, d_out);
+        CBL_LAUNCH(gather_u8_kernel, (unsigned)div_up(div_up(n, (uint64_t)4), (uint64_t)256), 256, 0, st_, d_src, d_pos, n, d_out);
         CUDA_CHECK(cudaStreamSynchronize(st_));
     }
 

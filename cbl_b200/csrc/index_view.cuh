@@ -25,6 +25,12 @@ namespace cbl {
 #ifndef CBL_L2_POLICY
 #define CBL_L2_POLICY 1
 #endif
+// DRAM fetch size of a probe load.  Measured on B200 (scripts/ubench/dram_gran.cu): a plain ld.global.nc that misses
+// L2 pulls the whole 128-byte line from HBM (125 B of DRAM traffic per random 32-byte read), the .L2::64B qualifier
+// halves that (63 B); cudaLimitMaxL2FetchGranularity changes nothing.  64B is the smallest size PTX offers.
+#ifndef CBL_L2_FETCH_Q
+#define CBL_L2_FETCH_Q ".L2::64B"
+#endif
 __device__ __forceinline__ uint64_t l2_policy_keep() {
     uint64_t p;
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -38,7 +44,7 @@ __device__ __forceinline__ uint64_t l2_policy_stream() {
 __device__ __forceinline__ uint2 ldg_keep(const uint2* p) {
 #if CBL_L2_POLICY
     uint2 v;
-    asm("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(l2_policy_keep()));
+    asm("ld.global.nc.L2::cache_hint" CBL_L2_FETCH_Q ".v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(l2_policy_keep()));
     return v;
 #else
     return __ldg(p);
@@ -47,7 +53,7 @@ __device__ __forceinline__ uint2 ldg_keep(const uint2* p) {
 __device__ __forceinline__ int ldg_keep(const int8_t* p) {
 #if CBL_L2_POLICY
     int v;
-    asm("ld.global.nc.L2::cache_hint.s8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_keep()));
+    asm("ld.global.nc.L2::cache_hint" CBL_L2_FETCH_Q ".s8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_keep()));
     return v;
 #else
     return (int)__ldg(p);
@@ -56,7 +62,7 @@ __device__ __forceinline__ int ldg_keep(const int8_t* p) {
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 #if CBL_L2_POLICY
     uint4 v;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint" CBL_L2_FETCH_Q ".v4.u32 {%0, %1, %2, %3}, [%4], %5;"
         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(l2_policy_stream()));
     return v;
 #else

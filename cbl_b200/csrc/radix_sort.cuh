@@ -329,9 +329,23 @@ __global__ void __launch_bounds__(256) route_hist_kernel(const W* __restrict__ k
     }
 }
 
+// answers back into read order.  The byte reads are scattered: fetch 64 B instead of the default 128-byte line per
+// L2 miss (see CBL_L2_FETCH_Q in index_view.cuh), four answers per thread so the output store is one word.
 static __global__ void gather_u8_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ pos, uint64_t n, uint8_t* __restrict__ out) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = src[pos[i]];
+    const uint64_t i4 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= n) return;
+    auto ld = [&](uint32_t p) {
+        uint32_t v;
+        asm("ld.global.nc.L1::no_allocate.L2::64B.u8 %0, [%1];" : "=r"(v) : "l"(src + p));
+        return v;
+    };
+    if (i4 + 4 <= n && ((uintptr_t)(out + i4) & 3) == 0 && ((uintptr_t)(pos + i4) & 15) == 0) {
+        const uint4 p = *reinterpret_cast<const uint4*>(pos + i4);
+        const uint32_t a = ld(p.x), b = ld(p.y), c = ld(p.z), d = ld(p.w);
+        *reinterpret_cast<uint32_t*>(out + i4) = a | (b << 8) | (c << 16) | (d << 24);
+    } else {
+        for (uint64_t i = i4; i < n && i < i4 + 4; i++) out[i] = (uint8_t)ld(pos[i]);
+    }
 }
 
 }  // namespace cbl

@@ -111,11 +111,14 @@ template <> __device__ __forceinline__ u128 cut_window<u128>(uint64_t A, uint64_
 // words, bucket ranges, correction bytes, suffix windows), each stage issuing U independent loads.
 // Measured on B200: U = 1 with high occupancy (40 registers) beats U = 2 / 4 (80 / 120 registers);
 // only U = 1 is instantiated.
+#ifndef CBL_SW_MIN_BLOCKS_WORDS
+#define CBL_SW_MIN_BLOCKS_WORDS 24   // word-level probe (MODE 3): 32 blocks (32 registers, no spills) measured 24.4 vs 19.3 ms: more warps thrash L1/L2
+#endif
 #ifndef CBL_SW_MIN_BLOCKS
 #define CBL_SW_MIN_BLOCKS 24   // fused probe: latency bound, occupancy beats a few spilled registers (measured)
 #endif
 template <class W, class Suf, int MODE, bool BRUTE, int WB, int U>
-__global__ void __launch_bounds__(SW_THREADS, ((MODE == 1 || MODE == 3) && U == 1) ? CBL_SW_MIN_BLOCKS : 1) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
+__global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN_BLOCKS_WORDS : ((MODE == 1 && U == 1) ? CBL_SW_MIN_BLOCKS : 1)) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
                                                                uint8_t* __restrict__ out_flags, IndexView<Suf> ix,
                                                                unsigned long long* __restrict__ err_pos, ShardArgs<W> sa) {
     static_assert(32 % U == 0, "U must divide 32");
@@ -321,7 +324,13 @@ __global__ void __launch_bounds__(SW_THREADS, ((MODE == 1 || MODE == 3) && U == 
                 }
                 Suf e[U][WN];
 #pragma unroll
-                for (int u = 0; u < U; u++) load_window<Suf, WB>(ix.suf + (g[u] & ~(uint32_t)(WN - 1)), e[u]);
+                for (int u = 0; u < U; u++) {
+#if defined(CBL_ABLATE_WINDOWS)   // developer ablation (wrong answers): no suffix-window traffic, tables only
+                    for (int i = 0; i < WN; i++) e[u][i] = s[u];
+#else
+                    load_window<Suf, WB>(ix.suf + (g[u] & ~(uint32_t)(WN - 1)), e[u]);
+#endif
+                }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     int r = 0;
