@@ -88,7 +88,13 @@ public:
         P_.suffix_bits = P_.bits + P_.pos_bits - cfg.prefix_bits;
         P_.canonical = cfg.canonical;
         CUDA_CHECK(cudaSetDevice(cfg.device));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        if (env_u64("CBL_STREAM_HIGH_PRIORITY", 0)) {   // the sharded pipeline's router handle: its CTAs are placed first
+            int lo_p = 0, hi_p = 0;
+            CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+            CUDA_CHECK(cudaStreamCreateWithPriority(&st_, cudaStreamNonBlocking, hi_p));
+        } else {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        }
         for (auto& s : side_) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, cfg.device));
@@ -272,7 +278,9 @@ public:
         ShardArgs<W> sa{};
         sa.in_words = d_words;
         sa.n_in = n;
-        const unsigned grid = (unsigned)std::min<uint64_t>(div_up(n, CHUNK_KMERS), 1u << 30);
+        // CBL_WORDS_GRID / CBL_ROUTE_GRID cap the grids (the kernels stride over the chunks) so that the owner-side probe and
+        // the next sub-batch's route kernel can be co-resident on every SM (sharded pipeline, cbl_b200/sharded.py)
+        const unsigned grid = (unsigned)std::min<uint64_t>(div_up(n, CHUNK_KMERS), env_u64("CBL_WORDS_GRID", 1u << 30));
         CBL_LAUNCH((seq_words_kernel<W, Suf, 3, false, CBL_PROBE_WB, 1>), grid, SW_THREADS, 0, s, SeqBatch{}, P_, (W*)nullptr, d_flags, view(),
                    (unsigned long long*)nullptr, sa);
     }
@@ -1025,7 +1033,7 @@ public:
         sa.cnt = cnt.get();
         sa.pos = d_pos;
         sa.cap = cap;
-        const unsigned grid = (unsigned)std::min<uint64_t>(dp.batch.n_chunks, 1u << 30);
+        const unsigned grid = (unsigned)std::min<uint64_t>(dp.batch.n_chunks, env_u64("CBL_ROUTE_GRID", 1u << 30));
         CBL_LAUNCH((seq_words_kernel<W, Suf, 2, false, 32, 1>), grid, SW_THREADS, 0, st_, dp.batch, P_, (W*)nullptr, (uint8_t*)nullptr, view(),
                    cnt.get() + 16, sa);
         unsigned long long h[17];

@@ -155,6 +155,8 @@ class PeerExchange:
     regions of ``cap`` bytes, region d written by owner d only, answer j of region d belonging to word j of
     region s at owner d."""
 
+    SLOTS = 2   # buffer sets: sub-batch b of a pipelined query uses set b & 1 (route of b + 1 overlaps the probe of b)
+
     def __init__(self, cbl, group, rank: int, world: int, device):
         self.cbl, self.group, self.rank, self.world, self.device = cbl, group, rank, world, device
         self.word_bytes = cbl.word_bytes()
@@ -201,17 +203,29 @@ class PeerExchange:
         self.cap = max((int(cap_words) + 2047) // 2048 * 2048, self.cap)
         if self.world * self.cap >= 1 << 32:
             raise ValueError("batch too large for one exchange: split the reads into smaller batches")
-        self.own_recv, h_recv = self.cbl.peer_alloc(self.world * self.cap * self.word_bytes)
-        self.own_back, h_back = self.cbl.peer_alloc(self.world * self.cap)
+        self.own_recv, h_recv = self.cbl.peer_alloc(self.SLOTS * self.world * self.cap * self.word_bytes)
+        self.own_back, h_back = self.cbl.peer_alloc(self.SLOTS * self.world * self.cap)
         handles = [None] * self.world
         dist.all_gather_object(handles, (h_recv, h_back), group=self.group)
         self.peer_recv = [self.own_recv if r == self.rank else self.cbl.peer_open(handles[r][0]) for r in range(self.world)]
         self.peer_back = [self.own_back if r == self.rank else self.cbl.peer_open(handles[r][1]) for r in range(self.world)]
         self.barrier()
 
-    def my_regions(self) -> List[int]:
-        """my region inside every owner's receive buffer"""
-        return [p + self.rank * self.cap * self.word_bytes for p in self.peer_recv]
+    def my_regions(self, slot: int = 0) -> List[int]:
+        """my region inside every owner's receive buffer (buffer set ``slot``)"""
+        return [p + (slot * self.world + self.rank) * self.cap * self.word_bytes for p in self.peer_recv]
+
+    def recv_region(self, src: int, slot: int = 0) -> int:
+        """region of my receive buffer that rank ``src`` writes"""
+        return self.own_recv + (slot * self.world + src) * self.cap * self.word_bytes
+
+    def answer_region(self, src: int, slot: int = 0) -> int:
+        """my region inside rank ``src``'s answer buffer"""
+        return self.peer_back[src] + (slot * self.world + self.rank) * self.cap
+
+    def answers(self, slot: int = 0) -> int:
+        """my own answer buffer (what pos[] of seq_route_dev indexes)"""
+        return self.own_back + slot * self.world * self.cap
 
     def close(self):
         if self.peer_recv or self.own_recv:
@@ -329,20 +343,118 @@ class ShardedCBL:
         """Per-k-mer answers (uint8 device tensor) for this rank's reads, in the reference's order
         (src/cbl.rs:311-324)."""
         if self.peer is not None:
-            px, cbl = self.peer, self.engine.cbl
-            C, pos = self._peer_route_seqs(d_buf, offsets, want_pos=True)
-            for s in range(self.world):   # region s of my receive buffer -> my region of rank s's answer buffer
-                n_s = int(C[s, self.rank])
-                if n_s:
-                    cbl.words_op_dev(0, px.own_recv + s * px.cap * px.word_bytes, n_s, px.peer_back[s] + self.rank * px.cap)
-            px.barrier()                                            # all answers have landed
-            n = pos.shape[0]
-            out = torch.empty(n, dtype=torch.uint8, device=self.device)
-            if n:
-                cbl.gather_u8_dev(px.own_back, pos.data_ptr(), n, out.data_ptr())
-            return out
+            return self._peer_contains(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
         words = self.engine.seq_words(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
         return self.contains_words(words)
+
+    # sub-batches of one contains_seqs call (same on every rank: the collectives must pair up).  Measured on 2 x B200
+    # (bench.py, 1 Gbp per rank): 4 sub-batches 53.6 ms per step, 1 sub-batch 50.7 ms — the route and probe kernels contend
+    # for the same SM resources when co-resident (each slows down by what the other takes), so the default is 1.
+    PIPE = 1
+
+    def _peer_contains(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
+        """Pipelined query over peer memory.  The reads are cut into PIPE sub-batches of whole records.  Sub-batch b:
+        (1) fused encode + necklace + route on the ROUTER handle's stream (integer-pipe bound), words stored into the
+        owners' buffer set b & 1; (2) count matrix exchange = "all words of b have landed"; (3) the owner-side probe of b
+        (memory bound) runs on the index handle's stream in a worker thread WHILE the main thread routes b + 1 — the two
+        kernels share the SMs the way the two halves of the single-GPU fused kernel do; (4) the answers of b are
+        gathered into read order after the next exchange, which every rank enters only after its probe of b is
+        complete.  A region overflow anywhere makes every rank start over with larger regions."""
+        import threading
+
+        import time
+
+        trace = os.environ.get("CBL_SHARD_TRACE") and self.rank == 0
+        t_last = [time.perf_counter()]
+
+        def mark(what):
+            if trace:
+                now = time.perf_counter()
+                print(f"[shard trace] {what}: {(now - t_last[0]) * 1e3:.2f} ms", flush=True)
+                t_last[0] = now
+
+        px, cbl, router = self.peer, self.engine.cbl, self._router()
+        n_rec = len(offsets) - 1
+        kpr = np.array([max(int(offsets[i + 1] - offsets[i]) - self.k + 1, 0) for i in range(n_rec)], dtype=np.int64)
+        total = int(kpr.sum())
+        pipe = max(1, int(os.environ.get("CBL_PIPE", self.PIPE)))
+        # record ranges with about the same number of k-mers (ranges may be empty on a rank with few records)
+        csum = np.concatenate([[0], np.cumsum(kpr)])
+        cuts = [int(np.searchsorted(csum, total * b / pipe, side="left")) for b in range(pipe)] + [n_rec]
+        cuts = [min(max(c, 0), n_rec) for c in cuts]
+        for i in range(1, len(cuts)):
+            cuts[i] = max(cuts[i], cuts[i - 1])
+        sub_n = [int(csum[cuts[b + 1]] - csum[cuts[b]]) for b in range(pipe)]
+        # doubles as the barrier "every rank is done with the buffers of the previous call"
+        n_max = int(px.all_counts(np.array([max(sub_n)], dtype=np.uint64)).max())
+        cap = int(n_max / self.world * float(os.environ.get("CBL_ROUTE_SLACK", self.SLACK))) + 4096
+        mark("plan + first count exchange")
+        out = torch.empty(total, dtype=torch.uint8, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        mark("alloc out")
+
+        def probe(C, slot):
+            for s_ in range(self.world):   # region s of my receive buffer -> my region of rank s's answer buffer
+                n_s = int(C[s_, self.rank])
+                if n_s:
+                    cbl.words_op_dev(0, px.recv_region(s_, slot), n_s, px.answer_region(s_, slot))
+
+        while True:
+            px.ensure(cap)
+            worker, prev, overflow = None, None, 0
+            for b in range(pipe):
+                slot = b & 1
+                r0, r1 = cuts[b], cuts[b + 1]
+                pos = torch.empty(sub_n[b], dtype=torch.int32, device=self.device)
+                if sub_n[b]:
+                    torch.cuda.current_stream(self.device).synchronize()   # pos is allocated before the router's stream writes it
+                    counts = router.seq_route_dev(d_buf, offsets[r0:r1 + 1], self.splitters_u32, px.my_regions(slot), px.cap, pos.data_ptr())
+                else:
+                    counts = np.zeros(self.world, dtype=np.uint64)
+                mark(f"route {b}")
+                if worker is not None:
+                    worker.join()
+                mark(f"join probe {b - 1}")
+                C = px.all_counts(counts)        # words of b have landed everywhere; so have the answers of b - 1
+                mark(f"count exchange {b}")
+                if prev is not None:
+                    self._gather(router, px, prev, out)
+                    prev = None
+                if int(C.max()) > px.cap:
+                    overflow = int(C.max())
+                    break
+                worker = threading.Thread(target=probe, args=(C, slot))
+                worker.start()
+                prev = (slot, pos, int(csum[r0]), sub_n[b])
+            if worker is not None:
+                worker.join()
+            mark("join last probe")
+            px.barrier()                         # the answers of the last sub-batch have landed
+            mark("barrier")
+            if not overflow:
+                if prev is not None:
+                    self._gather(router, px, prev, out)
+                mark("gather")
+                return out
+            cap = int(overflow * 1.1) + 4096     # a region overflowed somewhere: everybody retries
+
+    @staticmethod
+    def _gather(router, px, prev, out):
+        slot, pos, start, n = prev
+        if n:
+            router.gather_u8_dev(px.answers(slot), pos.data_ptr(), n, out.data_ptr() + start)
+
+    def _router(self):
+        """second handle (empty set, own CUDA stream) that runs the fused route kernel and the answer gather"""
+        if getattr(self, "_router_cbl", None) is None:
+            from .cbl import CBL
+
+            os.environ["CBL_STREAM_HIGH_PRIORITY"] = "1"   # read by the handle's constructor only
+            try:
+                self._router_cbl = CBL(self.k, self.t_bits, self.prefix_bits, self.canonical, self.device.index)
+            finally:
+                del os.environ["CBL_STREAM_HIGH_PRIORITY"]
+        return self._router_cbl
 
     # host-buffer front ends (what a user of the reference calls): copy, then the device path
     def insert_seqs(self, buf: np.ndarray, offsets: np.ndarray) -> None:
