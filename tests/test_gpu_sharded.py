@@ -22,8 +22,10 @@ WORKER = textwrap.dedent(
 
     K, TB, PB, CANON, MODE = {k}, {tb}, {pb}, {canon}, {mode!r}
     os.environ["CBL_EXCHANGE"] = MODE.split("-")[0]
-    if MODE == "peer-tight":   # regions too small at first: the overflow / retry path of the fused route
+    if "tight" in MODE:   # regions too small at first: the overflow / retry path of the fused route
         os.environ["CBL_ROUTE_SLACK"] = "0.7"
+    if "pipe" in MODE:    # pipelined query: 3 sub-batches, route of b + 1 overlapping the probe of b, two buffer sets
+        os.environ["CBL_PIPE"] = "3"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     torch.cuda.set_device(0)
@@ -56,8 +58,9 @@ WORKER = textwrap.dedent(
     # a larger batch forces the peer buffers to grow (collective re-map)
     big = util.random_dna(900000, seed=5 + rank)
     bd = torch.from_numpy(big).to(dev)
-    got = sh.contains_seqs_dev(bd.data_ptr(), np.array([0, len(big)], dtype=np.uint64)).cpu().numpy()
-    assert np.array_equal(got, ref.contains_seq(big))
+    got = sh.contains_seqs_dev(bd.data_ptr(), np.array([0, 200000, 500000, 650000, len(big)], dtype=np.uint64)).cpu().numpy()
+    exp = np.concatenate([ref.contains_seq(big[a:b]) for a, b in ((0, 200000), (200000, 500000), (500000, 650000), (650000, len(big)))])
+    assert np.array_equal(got, exp)
     r0 = torch.from_numpy(reads[0]).to(dev)
     if rank == 0:
         sh.remove_seqs_dev(r0.data_ptr(), np.array([0, 100000, len(reads[0])], dtype=np.uint64))
@@ -74,7 +77,8 @@ WORKER = textwrap.dedent(
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("k,tb,pb,canon,mode", [(25, 64, 24, False, "peer"), (31, 128, 24, True, "peer"), (59, 128, 28, False, "peer"),
-                                                 (25, 64, 24, True, "peer-tight")])
+                                                 (25, 64, 24, True, "peer-tight"), (25, 64, 24, False, "peer-pipe"),
+                                                 (31, 128, 24, True, "peer-pipe-tight")])
 def test_sharded_two_ranks_one_gpu(tmp_path, k, tb, pb, canon, mode):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT, k=k, tb=tb, pb=pb, canon=canon, mode=mode))
