@@ -72,26 +72,33 @@ def exchange(send: torch.Tensor, send_counts: torch.Tensor, group=None):
     return recv, recv_counts
 
 
-def equal_mass_splitters(prefixes: torch.Tensor, world: int, tail_cost: float = 1.0, tail_mass: float = 0.125) -> torch.Tensor:
+def equal_mass_splitters(prefixes: torch.Tensor, world: int, tail_cost: float = 1.0, knee: float = 0.625) -> torch.Tensor:
     """world-1 splitters s.t. each range [s_{i-1}, s_i) holds ~1/world of the sample's COST.
 
-    With ``tail_cost == 1`` cost = mass (every word counts 1).  Necklace prefixes are so skewed that the
-    last ``tail_mass`` of the words spreads over > 90 % of the prefix space: the shard that owns this tail holds
-    millions of tiny buckets, its bucket tables do not fit L2 and every look-up there costs an extra DRAM access
-    (measured on 8 x B200: probe 34 ms per 1 G words on the last rank, 22 ms on the others; 2 GPUs: 22.7 vs 19.8 ms).
-    ``tail_cost`` is the relative cost of a word in that tail; the splitters then equalise cost, not count."""
+    With ``tail_cost == 1`` cost = mass (every word counts 1).  Measured on 8 x B200 with equal-mass splitters (K=25,
+    500 M k-mers per rank, 1.06 G look-ups per rank and step): the owner-side probe takes 22 ns per 1000 words on rank 0
+    and grows steadily to 34 ns on ranks 5-7 — the shorter the leading zero run of a necklace, the more structure its
+    suffixes have and the less exact the slot prediction (more suffix windows per look-up).  The model used here: the
+    cost of a word rises linearly from 1 at the low end of the sorted sample to ``tail_cost`` at mass quantile ``knee``
+    and stays there; the splitters equalise cost, not count."""
     if world == 1:
         return prefixes.new_empty(0)
     srt, _ = torch.sort(prefixes)
     n = srt.numel()
-    n_tail = int(n * tail_mass) if tail_cost != 1.0 else 0
-    n_head = n - n_tail
-    total = n_head + tail_cost * n_tail
+    a = (tail_cost - 1.0) / (2.0 * knee)            # cumulative cost C(q) = q + a q^2 (q <= knee), linear beyond
+
+    def cum(q):
+        return q + a * q * q if q <= knee else knee + a * knee * knee + tail_cost * (q - knee)
+
+    total = cum(1.0)
     idx = []
     for i in range(1, world):
-        c = total * i / world                      # cost below splitter i
-        j = c if c <= n_head else n_head + (c - n_head) / tail_cost
-        idx.append(min(int(j), n - 1))
+        c = total * i / world
+        if c <= cum(knee):
+            q = c if a == 0.0 else (-1.0 + (1.0 + 4.0 * a * c) ** 0.5) / (2.0 * a)
+        else:
+            q = knee + (c - cum(knee)) / tail_cost
+        idx.append(min(int(q * n), n - 1))
     sp = srt[torch.tensor(idx, device=srt.device)]
     # strictly increasing splitters keep every range non-empty in prefix space
     for i in range(1, sp.numel()):
@@ -319,8 +326,8 @@ class ShardedCBL:
                 return C, pos
             cap = int(int(C.max()) * 1.1) + 4096                     # a region overflowed somewhere: everybody retries
 
-    TAIL_COST = 1.5   # relative probe cost of a word in the sparse tail of the prefix space (equal_mass_splitters)
-    SLACK = 1.15   # region capacity over the even share (equal-mass splitters keep the spread at a few per cent)
+    TAIL_COST = 1.5   # relative probe cost of a word beyond the knee of the sorted prefix sample (equal_mass_splitters)
+    SLACK = 1.3    # region capacity over the even share (cost-weighted splitters give the first rank ~20 % more words)
 
     def _mutate(self, op: int, d_buf: int, offsets: np.ndarray) -> None:
         if self.peer is not None:
@@ -409,10 +416,14 @@ class ShardedCBL:
         mark("alloc out")
 
         def probe(C, slot):
+            t_p = time.perf_counter()
             for s_ in range(self.world):   # region s of my receive buffer -> my region of rank s's answer buffer
                 n_s = int(C[s_, self.rank])
                 if n_s:
                     cbl.words_op_dev(0, px.recv_region(s_, slot), n_s, px.answer_region(s_, slot))
+            if os.environ.get("CBL_SHARD_TRACE"):
+                print(f"[shard trace] rank {self.rank}: probe of {int(C[:, self.rank].sum())} words {(time.perf_counter() - t_p) * 1e3:.2f} ms, "
+                      f"{cbl.num_buckets()} buckets, {cbl.count()} k-mers", flush=True)
 
         while True:
             px.ensure(cap)

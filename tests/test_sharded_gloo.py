@@ -45,11 +45,11 @@ def test_word_prefixes_and_route():
     s = equal_mass_splitters(torch.arange(1000), 4)
     assert s.tolist() == [250, 500, 750]
     assert equal_mass_splitters(torch.zeros(100, dtype=torch.int64), 3).tolist() == [0, 1]
-    # cost-weighted splitters: the last eighth of the sample counts 1.5x, so the ranges equalise cost, not count
+    # cost-weighted splitters: cost rises from 1 to 1.5 over the first 62.5 % of the sorted sample, ranges equalise cost
     w = equal_mass_splitters(torch.arange(8000), 8, tail_cost=1.5)
     edges = [0] + w.tolist() + [8000]
-    cost = [sum(1.5 if x >= 7000 else 1.0 for x in range(a, b)) for a, b in zip(edges, edges[1:])]
-    assert max(cost) - min(cost) <= 2.5 and edges[-2] > 7000 and edges[1] > 1000
+    cost = [sum(1.0 + 0.5 * min(x / 5000.0, 1.0) for x in range(a, b)) for a, b in zip(edges, edges[1:])]
+    assert max(cost) - min(cost) <= 3.0 and edges[1] > 1150 and edges[-1] - edges[-2] < 900
 
 
 WORKER = textwrap.dedent(
