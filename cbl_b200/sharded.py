@@ -175,10 +175,11 @@ class PeerExchange:
     regions of ``cap`` bytes, region d written by owner d only, answer j of region d belonging to word j of
     region s at owner d."""
 
-    SLOTS = 2   # buffer sets: sub-batch b of a pipelined query uses set b & 1 (route of b + 1 overlaps the probe of b)
 
     def __init__(self, cbl, group, rank: int, world: int, device):
         self.cbl, self.group, self.rank, self.world, self.device = cbl, group, rank, world, device
+        # buffer sets: sub-batch b of a pipelined query (CBL_PIPE > 1) uses set b & 1 (route of b + 1 overlaps the probe of b)
+        self.SLOTS = 2 if int(os.environ.get("CBL_PIPE", "1")) > 1 else 1
         self.word_bytes = cbl.word_bytes()
         backend = dist.get_backend(group)
         self.ctrl = torch.device("cpu") if backend == "gloo" else device
@@ -399,7 +400,7 @@ class ShardedCBL:
         n_rec = len(offsets) - 1
         kpr = np.array([max(int(offsets[i + 1] - offsets[i]) - self.k + 1, 0) for i in range(n_rec)], dtype=np.int64)
         total = int(kpr.sum())
-        pipe = max(1, int(os.environ.get("CBL_PIPE", self.PIPE)))
+        pipe = max(1, int(os.environ.get("CBL_PIPE", self.PIPE))) if px.SLOTS > 1 else 1
         # record ranges with about the same number of k-mers (ranges may be empty on a rank with few records)
         csum = np.concatenate([[0], np.cumsum(kpr)])
         cuts = [int(np.searchsorted(csum, total * b / pipe, side="left")) for b in range(pipe)] + [n_rec]
