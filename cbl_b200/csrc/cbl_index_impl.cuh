@@ -371,10 +371,14 @@ public:
         DevBuf<unsigned> fail(1, st_);
         fail.zero();
         const int shift = 8 * (n_digits - n_pass);
+        // nominal tile: leave room for segments 3x longer than the longest one expected, at least 512 keys
+        const double est_seg = (double)n * (double)P_.bits / std::ldexp(1.0, key_bits - shift);
+        const int room = (int)std::min<double>(SsTile<W>::CAP / 2, std::max<double>(512.0, std::ceil(3.0 * est_seg / 256.0) * 256.0));
+        const int tile = SsTile<W>::CAP - room;
         if (shift <= 32)
-            CBL_LAUNCH((seg_sort_kernel<W, true>), (unsigned)div_up(n, SsTile<W>::T), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, fail.get());
+            CBL_LAUNCH((seg_sort_kernel<W, true>), (unsigned)div_up(n, (uint64_t)tile), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, fail.get(), tile);
         else
-            CBL_LAUNCH((seg_sort_kernel<W, false>), (unsigned)div_up(n, SsTile<W>::T), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, fail.get());
+            CBL_LAUNCH((seg_sort_kernel<W, false>), (unsigned)div_up(n, (uint64_t)tile), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, fail.get(), tile);
         unsigned h_fail = 0;
         CUDA_CHECK(cudaMemcpyAsync(&h_fail, fail.get(), sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));

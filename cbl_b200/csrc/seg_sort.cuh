@@ -26,7 +26,7 @@ constexpr int SS_THREADS = 512;
 template <class W> struct SsTile {
     static constexpr int ITEMS = sizeof(W) == 8 ? 11 : 7;   // odd: blocked shared-memory access without bank conflicts
     static constexpr int CAP = SS_THREADS * ITEMS;          // keys one CTA can stage
-    static constexpr int T = CAP / 2;                       // nominal keys per tile; longest segment always handled = CAP - T
+    static constexpr int T = CAP / 2;                       // smallest nominal tile (keys a CTA owns); longest segment always handled = CAP - tile
     static constexpr int LIM = CAP + 1;                     // staged slots: slot j holds in[t0 - 1 + j]
     static constexpr size_t OFF_CNT = ((size_t)LIM * sizeof(W) + 15) & ~(size_t)15;
     static constexpr size_t OFF_SEG = OFF_CNT + (((size_t)(CAP + 1) * 4 + 15) & ~(size_t)15);
@@ -43,8 +43,10 @@ template <class W> __device__ __forceinline__ uint32_t low_top32(W key, int shif
 // LOW32: shift <= 32, so two words of one segment compare like their low 32 bits
 template <class W, bool LOW32>
 __global__ void __launch_bounds__(SS_THREADS, 2) seg_sort_kernel(const W* __restrict__ in, W* __restrict__ out, uint64_t n, int shift,
-                                                                 unsigned* __restrict__ fail) {
-    constexpr int ITEMS = SsTile<W>::ITEMS, CAP = SsTile<W>::CAP, T = SsTile<W>::T, LIM = SsTile<W>::LIM;
+                                                                 unsigned* __restrict__ fail, const int T) {
+    // T = nominal keys per tile (run-time, SsTile<W>::T <= T < CAP): the longest segment always handled is CAP - T, so the
+    // caller raises T when it expects short segments and a CTA then sorts close to CAP keys instead of CAP / 2
+    constexpr int ITEMS = SsTile<W>::ITEMS, CAP = SsTile<W>::CAP, LIM = SsTile<W>::LIM;
     extern __shared__ __align__(16) unsigned char ss_raw[];
     W* A = reinterpret_cast<W*>(ss_raw);                                                // [LIM] staging, later the binned keys
     uint32_t* cnt = reinterpret_cast<uint32_t*>(ss_raw + SsTile<W>::OFF_CNT);          // [CAP + 1] bin counters -> first slot of every bin
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(SS_THREADS, 2) seg_sort_kernel(const W* __rest
     __shared__ uint32_t s_tmp[33];
     __shared__ int s_a0, s_a1;
     const int t = threadIdx.x;
+    const W hi_mask = (W)~low_mask<W>(shift);   // two words belong to one segment iff they agree on these bits
     const uint64_t t0 = (uint64_t)blockIdx.x * T;
     if (t0 >= n) return;
     // slot one past the last key of the batch (the end of the data closes the last segment)
@@ -65,14 +68,12 @@ __global__ void __launch_bounds__(SS_THREADS, 2) seg_sort_kernel(const W* __rest
     // ---- 1. stage the nominal tile plus one chunk; a0 = first segment start inside the tile, a1 = first one after it
     int loaded = 0;                       // slots [0, loaded) are staged
     auto stage = [&](int upto) {          // upto <= min(LIM, jend)
-        for (int j = loaded + t; j < upto; j += SS_THREADS) {
-            const uint64_t g = t0 + (uint64_t)j;   // = global index + 1
-            A[j] = g >= 1 ? in[g - 1] : (W)0;
-        }
+        const W* const src = in + t0;               // slot j holds src[j - 1]; slot 0 of the first tile holds nothing
+        for (int j = loaded + t; j < upto; j += SS_THREADS) A[j] = (j > 0 || t0 > 0) ? src[(long long)j - 1] : (W)0;
     };
     auto find_bounds = [&](int upto) {    // segment starts among slots [loaded, upto); the end of the data counts for a1 only
         for (int j = max(loaded, 1) + t; j < upto; j += SS_THREADS) {
-            const bool bnd = (t0 + (uint64_t)j == 1) || (A[j] >> shift) != (A[j - 1] >> shift);
+            const bool bnd = (t0 + (uint64_t)j == 1) || ((A[j] ^ A[j - 1]) & hi_mask) != 0;
             if (bnd) atomicMin(j <= T ? &s_a0 : &s_a1, j);
         }
         if (t == 0 && jend <= upto) atomicMin(&s_a1, jend);
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(SS_THREADS, 2) seg_sort_kernel(const W* __rest
             key[i] = (W)0;
             if (e < m) {
                 key[i] = A[a0 + e];
-                if (e == 0 || (key[i] >> shift) != (A[a0 + e - 1] >> shift)) flags |= 1u << i;
+                if (e == 0 || ((key[i] ^ A[a0 + e - 1]) & hi_mask) != 0) flags |= 1u << i;
             }
         }
         uint32_t total;
@@ -135,7 +136,8 @@ __global__ void __launch_bounds__(SS_THREADS, 2) seg_sort_kernel(const W* __rest
         br[i] = 0;
         if (ITEMS * t + i < m) {
             const uint32_t st = seg_start[sidx[i]], len = seg_start[sidx[i] + 1] - st;
-            const uint32_t bin = st + __umulhi(low_top32<W>(key[i], shift), len);
+            const uint32_t k32 = LOW32 ? ((uint32_t)key[i] << (32 - shift)) : low_top32<W>(key[i], shift);   // shift in [1, 32] when LOW32
+            const uint32_t bin = st + __umulhi(k32, len);
             const uint32_t r = atomicAdd(&cnt[bin], 1u);
             br[i] = bin | (r << 16);
         }
