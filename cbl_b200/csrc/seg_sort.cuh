@@ -24,7 +24,10 @@ namespace cbl {
 
 constexpr int SS_THREADS = 512;
 template <class W> struct SsTile {
-    static constexpr int ITEMS = sizeof(W) == 8 ? 11 : 7;   // odd: blocked shared-memory access without bank conflicts
+#ifndef CBL_SS_ITEMS8
+#define CBL_SS_ITEMS8 11
+#endif
+    static constexpr int ITEMS = sizeof(W) == 8 ? CBL_SS_ITEMS8 : 7;   // odd: blocked shared-memory access without bank conflicts
     static constexpr int CAP = SS_THREADS * ITEMS;          // keys one CTA can stage
     static constexpr int T = CAP / 2;                       // smallest nominal tile (keys a CTA owns); longest segment always handled = CAP - tile
     static constexpr int LIM = CAP + 1;                     // staged slots: slot j holds in[t0 - 1 + j]
