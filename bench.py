@@ -254,6 +254,30 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def build_phase_roofline(build_prof, n_kmers, stored, peak):
+    """Per-kernel HBM roofline of the build (insert_seq) phases: algorithmic bytes of SURVEY 8d (u64 words W = 8,
+    u32 suffixes S = 4, PREFIX_BITS = 24) divided by the kernel's CUDA-event time.  The words kernel is integer-bound
+    (its roofline is the ALU pipe, see profiles/), listed for completeness."""
+    if not build_prof:
+        return None
+    W, S = 8, 4
+    per_launch = {
+        "seq_words_kernel": n_kmers * (1 + W),            # ASCII in, word out
+        "radix_hist_kernel": n_kmers * W,                  # one read of the words
+        "radix_pass_kernel": n_kmers * 2 * W,              # read + scatter per pass
+        "seg_sort_kernel": n_kmers * 2 * W,                # read + write, whatever the number of remaining bits
+        "merge_apply_kernel": n_kmers * W + stored * S + 3 * (1 << 24) * 4,   # batch words in, new suffixes out, per-prefix counters
+    }
+    out = {}
+    for name, rec in build_prof.items():
+        for key, nbytes in per_launch.items():
+            if name.startswith(key) and rec.get("ms"):
+                gbs = nbytes * rec["n"] / (rec["ms"] * 1e-3) / 1e9
+                out[key] = {"launches": rec["n"], "ms": rec["ms"], "algorithmic_bytes_per_launch": nbytes, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+    return out
+
+
+
 # ------------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------------
@@ -429,6 +453,11 @@ def run_ours(args):
         cpu = {"value": r["contains_kmers_per_s"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["sample"], "note": r["kind_note"],
                "insert_seq_kmers_per_s": r["insert_kmers_per_s"], "host_cores_available": os.cpu_count()}
 
+    build_roof = None
+    try:
+        build_roof = build_phase_roofline(build_prof, n_i_kmers, stored, peak)
+    except Exception as e:  # reporting only: never lose the bench line over it
+        build_roof = {"error": repr(e)}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -441,7 +470,7 @@ def run_ours(args):
                        "parallelism": "1 GPU" if world == 1 else f"prefix-range sharded x{world}, one all-to-all per batch"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "extra": {"wall_s_timed_region": wall, "insert_seq_kmers_per_s": n_i_kmers * world / t_build, "build_s": t_build, "kernel_ms": prof,
-                      "build_kernel_ms": build_prof,
+                      "build_kernel_ms": build_prof, "build_roofline": build_roof,
                       "build_s_warm_pool": t_build_warm,
                       "insert_seq_kmers_per_s_warm_pool": (n_i_kmers * world / t_build_warm) if t_build_warm else None},
         }
