@@ -58,6 +58,7 @@ SIGNATURES = {
     "cbl_seq_words_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t, vp]),
     "cbl_words_op_dev": (C.c_int32, [vp, C.c_int32, vp, C.c_size_t, vp]),
     "cbl_words_op_segments_dev": (C.c_int32, [vp, C.c_int32, vpp, u64p, C.c_uint32]),
+    "cbl_words_contains_segments_dev": (C.c_int32, [vp, vpp, u64p, vpp, C.c_uint32]),
     "cbl_export_words_dev": (C.c_int32, [vp, C.c_uint64, C.c_uint64, vp]),
     "cbl_route_words_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, vp, vp, u64p]),
     "cbl_gather_u8_dev": (C.c_int32, [vp, vp, vp, C.c_size_t, vp]),

@@ -265,6 +265,14 @@ class CBL:
         n = np.ascontiguousarray(seg_n, dtype=np.uint64)
         self._chk(self._L.cbl_words_op_segments_dev(self._h, op, C.cast(ptrs, vpp_t), n.ctypes.data_as(u64p), g))
 
+    def words_contains_segments_dev(self, seg_ptrs, seg_n, out_ptrs) -> None:
+        """Membership of the words of several device segments in ONE launch; answers of segment i -> out_ptrs[i]."""
+        g = len(seg_ptrs)
+        ptrs = (C.c_void_p * g)(*[int(x) for x in seg_ptrs])
+        outs = (C.c_void_p * g)(*[int(x) for x in out_ptrs])
+        n = np.ascontiguousarray(seg_n, dtype=np.uint64)
+        self._chk(self._L.cbl_words_contains_segments_dev(self._h, C.cast(ptrs, vpp_t), n.ctypes.data_as(u64p), C.cast(outs, vpp_t), g))
+
     def gather_u8_dev(self, d_src: int, d_pos: int, n: int, d_out: int) -> None:
         self._chk(self._L.cbl_gather_u8_dev(self._h, d_src, d_pos, n, d_out))
 

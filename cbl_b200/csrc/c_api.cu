@@ -394,6 +394,14 @@ int32_t cbl_words_op_segments_dev(cbl_t* h, int32_t op, const void* const* seg, 
         h->ix->sync();
     });
 }
+int32_t cbl_words_contains_segments_dev(cbl_t* h, const void* const* seg, const uint64_t* seg_n, uint8_t* const* seg_out, uint32_t n_seg) {
+    return guard(h, [&] {
+        need(h, "handle");
+        if (n_seg) { need(seg, "seg"); need(seg_n, "seg_n"); need(seg_out, "seg_out"); }
+        h->ix->words_contains_segments_dev(seg, seg_n, seg_out, n_seg);
+        h->ix->sync();
+    });
+}
 int32_t cbl_export_words_dev(cbl_t* h, uint64_t start, uint64_t count, void* d_out) {
     return guard(h, [&] { need(h, "handle"); if (count) need(d_out, "d_out"); h->ix->export_words_dev(start, count, 0, d_out); h->ix->sync(); });
 }

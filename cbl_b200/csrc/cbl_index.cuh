@@ -47,6 +47,7 @@ public:
     // words (already transformed) — used by the sharded multi-GPU path after the all-to-all
     virtual void words_op_dev(int op, const void* d_words, uint64_t n, uint8_t* d_out) = 0;
     virtual void words_op_segments_dev(int op, const void* const* seg, const uint64_t* seg_n, uint32_t n_seg) = 0;
+    virtual void words_contains_segments_dev(const void* const* seg, const uint64_t* seg_n, uint8_t* const* seg_out, uint32_t n_seg) = 0;
     // multi-GPU routing: stable partition of words by owner rank (dest = #splitters <= prefix)
     virtual void route_words_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* d_send,
                                  uint32_t* d_pos, uint64_t* counts) = 0;

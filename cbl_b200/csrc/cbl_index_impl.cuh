@@ -10,6 +10,8 @@
 #include <climits>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
 
 #include "index_ops.cuh"
 #include "merge_ops.cuh"
@@ -69,7 +71,6 @@ class Index final : public IIndex {
     DevBuf<uint2> dir_, bucket_range_;
     DevBuf<uint32_t> bucket_prefix_, bucket_off_;
     DevBuf<Suf> suf_;
-    bool use_merge_ = true;   // CBL_MUTATE=edits selects the first-generation probe/edit-list path (kept for A/B runs)
     DevBuf<int8_t> sub_;      // interpolation corrections for the membership probe, rebuilt lazily
     bool sub_valid_ = false;
     uint32_t nb_ = 0;
@@ -77,7 +78,25 @@ class Index final : public IIndex {
     uint32_t last_prefix_ = 0;  // prefix of the last bucket (for the reference's is_empty quirk)
     uint64_t n_dir_ = 0;  // directory words: 32 prefixes each
     uint64_t batch_kmers_;
+    bool sort_hybrid_ = true;   // CBL_SORT=lsd (read once, here): plain LSD passes instead of top passes + segment sort
     static constexpr uint64_t SUF_PAD = 16;  // suffix arrays are over-allocated: probe windows are 32-byte aligned loads
+    // pinned host staging of this handle: piece tables on their way in, status words on their way out.  A mutation
+    // enqueues ALL of its kernels and reads this block back with ONE synchronisation at its end.
+    struct HostStage {
+        uint8_t* p = nullptr;
+        size_t cap = 0;
+        void reserve(size_t bytes) {
+            if (bytes <= cap) return;
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+            CUDA_CHECK(cudaMallocHost((void**)&p, cap));
+        }
+        ~HostStage() { if (p) cudaFreeHost(p); }
+    } stage_;
+    cudaEvent_t stage_ev_ = nullptr;           // the last copy out of stage_ has completed
+    unsigned long long* h_status_ = nullptr;   // pinned: [0] merged elements, [1] buckets, [2] elements by the directory,
+                                               // [3] last prefix, [4] segment-sort fail flag, [5] non-ACGT byte offset
 
 public:
     explicit Index(const Config& cfg) : cfg_(cfg) {
@@ -96,10 +115,12 @@ public:
             CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         }
         for (auto& s : side_) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        cudaMemPool_t pool;
-        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, cfg.device));
-        uint64_t thr = UINT64_MAX;
-        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        if (env_u64("CBL_ARENA", 1) == 0) {   // cudaMallocAsync mode only: keep freed blocks in the driver's pool
+            cudaMemPool_t pool;
+            CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, cfg.device));
+            uint64_t thr = UINT64_MAX;
+            CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        }
         uint64_t bits = 1ull << cfg.prefix_bits;
         if (bits < 32) bits = 32;
         n_dir_ = bits / 32;
@@ -111,9 +132,10 @@ public:
         bucket_off_.zero();
         suf_.alloc(SUF_PAD, st_);
         suf_.zero();
-        sub_.alloc(4, st_);
+        sub_.alloc(8, st_);
         sub_.zero();
-        { const char* m = getenv("CBL_MUTATE"); use_merge_ = !(m && std::string(m) == "edits"); }
+        { const char* m = getenv("CBL_SORT"); sort_hybrid_ = !(m && std::string(m) == "lsd"); }
+        CUDA_CHECK(cudaMallocHost((void**)&h_status_, 8 * sizeof(unsigned long long)));
         batch_kmers_ = env_u64("CBL_BATCH_KMERS", sizeof(W) == 8 ? (1ull << 29) : (1ull << 28));   // sort buffers: 2 x 4.3 GB of the 180 GB
         if (batch_kmers_ > RS_MAX_KEYS) batch_kmers_ = RS_MAX_KEYS;
         if (batch_kmers_ < CHUNK_KMERS) batch_kmers_ = CHUNK_KMERS;
@@ -124,23 +146,30 @@ public:
             CUDA_CHECK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg.device));
             CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)mb << 20, (size_t)max_persist)));
         }
-        static bool attr_done = false;
-        if (!attr_done) {
-            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, ByteDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, ByteDigit<W>>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            CUDA_CHECK(cudaFuncSetAttribute((seg_sort_kernel<W, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SsTile<W>::SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute((seg_sort_kernel<W, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            CUDA_CHECK(cudaFuncSetAttribute((seg_sort_kernel<W, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SsTile<W>::SMEM));
-            CUDA_CHECK(cudaFuncSetAttribute((seg_sort_kernel<W, false>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_OR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_AND>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_SUB>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute((merge_apply_kernel<W, Suf, MERGE_XOR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute((radix_pass_kernel<W, false, DestDigit<W>, true>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            attr_done = true;
+        // opt-ins for > 48 KB of dynamic shared memory are per device (context): done once per (instantiation, device),
+        // under a lock so that handles may be created from several threads / on several GPUs of one process
+        {
+            static std::mutex mu;
+            static std::set<int> done;
+            std::lock_guard<std::mutex> lk(mu);
+            if (!done.count(cfg.device)) {
+                auto opt_in = [](auto kernel, size_t bytes) {
+                    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                };
+                opt_in(radix_pass_kernel<W, false, ByteDigit<W>>, 96 * 1024);
+                opt_in(radix_pass_kernel<W, false, DestDigit<W>>, 96 * 1024);
+                opt_in(radix_pass_kernel<W, false, DestDigit<W>, true>, 96 * 1024);
+                opt_in(seg_sort_kernel<W, true>, SsTile<W>::SMEM);
+                opt_in(seg_sort_kernel<W, false>, SsTile<W>::SMEM);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_OR, false>, 64 * 1024);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_SUB, false>, 64 * 1024);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_OR, true>, 64 * 1024);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_AND, true>, 64 * 1024);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_SUB, true>, 64 * 1024);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_XOR, true>, 64 * 1024);
+                done.insert(cfg.device);
+            }
         }
         CUDA_CHECK(cudaStreamSynchronize(st_));
     }
@@ -149,6 +178,8 @@ public:
         dir_.release(); bucket_range_.release(); bucket_prefix_.release(); bucket_off_.release(); suf_.release(); sub_.release();
         if (st_) { cudaStreamSynchronize(st_); arena::retire_stream(st_); cudaStreamDestroy(st_); }
         for (auto& s : side_) if (s) { cudaStreamSynchronize(s); arena::retire_stream(s); cudaStreamDestroy(s); }
+        if (h_status_) cudaFreeHost(h_status_);
+        if (stage_ev_) cudaEventDestroy(stage_ev_);
     }
 
     const Config& config() const override { return cfg_; }
@@ -174,7 +205,7 @@ public:
     // (re)build the probe's correction bytes if the set changed since they were last computed
     void ensure_sub() {
         if (sub_valid_) return;
-        const uint64_t n_slots = (n_ >> SUB_SHIFT) + 4;
+        const uint64_t n_slots = (n_ >> SUB_SHIFT) + 8;
         sub_.alloc(n_slots, st_);
         CBL_LAUNCH((build_sub_kernel<Suf>), (unsigned)div_up(n_slots, 256), 256, 0, st_, view(), P_.suffix_bits, sub_.get(), n_slots);
         sub_valid_ = true;
@@ -234,55 +265,121 @@ public:
     }
 
     struct DevPieces {
-        DevBuf<uint64_t> byte_off, out_off, chunk0;
-        DevBuf<uint32_t> kmers;
+        DevBuf<uint8_t> blob;   // [byte_off | out_off | chunk0 | kmers] of the pieces
         SeqBatch batch;
     };
-    // upload pieces [p0, p1) with out offsets rebased by out_base
+    // upload pieces [p0, p1) with out offsets rebased by out_base.  The tables go through the handle's pinned staging
+    // block, so the copies are true asynchronous DMA and the host does not wait for them.
     void upload_pieces(const PieceList& pl, size_t p0, size_t p1, uint64_t out_base, const uint8_t* d_seq, uint64_t n_bytes,
-                       DevPieces& dp, cudaStream_t s) const {
-        size_t np = p1 - p0;
-        std::vector<uint64_t> out(np), ch(np + 1);
-        for (size_t i = 0; i < np; i++) { out[i] = pl.out_off[p0 + i] - out_base; ch[i] = pl.chunk0[p0 + i] - pl.chunk0[p0]; }
-        ch[np] = pl.chunk0[p1] - pl.chunk0[p0];
-        dp.byte_off.alloc(np, s); dp.out_off.alloc(np, s); dp.chunk0.alloc(np + 1, s); dp.kmers.alloc(np, s);
-        CUDA_CHECK(cudaMemcpyAsync(dp.byte_off.get(), pl.byte_off.data() + p0, np * 8, cudaMemcpyHostToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(dp.out_off.get(), out.data(), np * 8, cudaMemcpyHostToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(dp.chunk0.get(), ch.data(), (np + 1) * 8, cudaMemcpyHostToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(dp.kmers.get(), pl.kmers.data() + p0, np * 4, cudaMemcpyHostToDevice, s));
-        CUDA_CHECK(cudaStreamSynchronize(s));  // `out`/`ch` are stack temporaries
+                       DevPieces& dp, cudaStream_t s) {
+        const size_t np = p1 - p0;
+        if (stage_ev_) CUDA_CHECK(cudaEventSynchronize(stage_ev_));   // the previous user of the staging block is done (normally long ago)
+        else CUDA_CHECK(cudaEventCreateWithFlags(&stage_ev_, cudaEventDisableTiming));
+        const size_t o_byte = 0, o_out = np * 8, o_ch = 2 * np * 8, o_km = (3 * np + 1) * 8;
+        stage_.reserve(o_km + np * 4);
+        uint64_t* h_byte = reinterpret_cast<uint64_t*>(stage_.p + o_byte);
+        uint64_t* h_out = reinterpret_cast<uint64_t*>(stage_.p + o_out);
+        uint64_t* h_ch = reinterpret_cast<uint64_t*>(stage_.p + o_ch);
+        uint32_t* h_km = reinterpret_cast<uint32_t*>(stage_.p + o_km);
+        for (size_t i = 0; i < np; i++) {
+            h_byte[i] = pl.byte_off[p0 + i];
+            h_out[i] = pl.out_off[p0 + i] - out_base;
+            h_ch[i] = pl.chunk0[p0 + i] - pl.chunk0[p0];
+            h_km[i] = pl.kmers[p0 + i];
+        }
+        h_ch[np] = pl.chunk0[p1] - pl.chunk0[p0];
+        // one device block, one copy: [byte_off | out_off | chunk0 | kmers]
+        dp.blob.alloc(o_km + np * 4, s);
+        CUDA_CHECK(cudaMemcpyAsync(dp.blob.get(), stage_.p, o_km + np * 4, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaEventRecord(stage_ev_, s));
         dp.batch.seq = d_seq; dp.batch.seq_end = d_seq + n_bytes;
-        dp.batch.piece_byte = dp.byte_off.get(); dp.batch.piece_out = dp.out_off.get();
-        dp.batch.piece_kmers = dp.kmers.get(); dp.batch.piece_chunk0 = dp.chunk0.get();
-        dp.batch.n_pieces = (uint32_t)np; dp.batch.n_chunks = ch[np];
+        dp.batch.piece_byte = reinterpret_cast<const uint64_t*>(dp.blob.get() + o_byte);
+        dp.batch.piece_out = reinterpret_cast<const uint64_t*>(dp.blob.get() + o_out);
+        dp.batch.piece_chunk0 = reinterpret_cast<const uint64_t*>(dp.blob.get() + o_ch);
+        dp.batch.piece_kmers = reinterpret_cast<const uint32_t*>(dp.blob.get() + o_km);
+        dp.batch.n_pieces = (uint32_t)np; dp.batch.n_chunks = h_ch[np];
     }
 
+    // plan of the LSD part of the batch sort, known before the words exist (it only depends on their number)
+    struct SortPlan {
+        int n_digits = 0, n_pass = 0, first = 0;   // LSD passes over digits [first, first + n_pass); n_pass == n_digits: plain LSD sort
+    };
+    SortPlan plan_sort(uint64_t n) const {
+        SortPlan sp;
+        const int key_bits = P_.bits + P_.pos_bits;
+        sp.n_digits = (key_bits + 7) / 8;
+        sp.n_pass = sp.n_digits;
+        // Hybrid (default): LSD passes over the top digits only, then the in-shared-memory segment sort (seg_sort.cuh).
+        // The number of passes is chosen so that the largest group of words sharing their sorted top bits fits a segment
+        // tile: for k-mer data the most frequent b-bit head of a necklace word has mass ~ 2K / 2^b.  Any other
+        // distribution is still sorted exactly: a segment that does not fit raises the fail flag and the batch is
+        // re-sorted by the plain LSD passes.
+        if (sort_hybrid_) {
+            for (int c = 1; c < sp.n_digits - 1; c++) {   // c LSD passes leave 8 * (n_digits - c) low bits to the segment sort
+                const int b = key_bits - 8 * (sp.n_digits - c);
+                const double est = (double)n * (double)P_.bits / std::ldexp(1.0, b);
+                if (est * 1.5 <= (double)SsTile<W>::T) { sp.n_pass = c; break; }
+            }
+        }
+        sp.first = sp.n_digits - sp.n_pass;
+        return sp;
+    }
     // launches the fused encode + necklace (+ probe) kernel (no synchronisation); *err must hold
-    // ULLONG_MAX on entry and receives the smallest offending byte offset if a non-ACGT byte is seen
-    void launch_seq_words(const SeqBatch& b, int mode, bool brute, W* d_words, uint8_t* d_flags, unsigned long long* err, cudaStream_t s) {
+    // ULLONG_MAX on entry and receives the smallest offending byte offset if a non-ACGT byte is seen.
+    // hist != null (mode 0): the kernel also counts the digits of plan's LSD passes (hist zeroed by the caller).
+    void launch_seq_words(const SeqBatch& b, int mode, bool brute, W* d_words, uint8_t* d_flags, unsigned long long* err, cudaStream_t s,
+                          unsigned long long* hist = nullptr, const SortPlan* plan = nullptr) {
         if (b.n_chunks == 0) return;
         unsigned grid = (unsigned)std::min<uint64_t>(b.n_chunks, 1u << 30);
         IndexView<Suf> v = view();
-        const ShardArgs<W> sa{};
+        ShardArgs<W> sa{};
         if (mode == 0) {
+            const uint64_t persist = env_u64("CBL_WORDS_PERSIST", 0);   // developer knob: persistent grid 0 never (measured: one CTA per chunk is 0.8 ms faster per 500 M k-mers), 1 always, 2 with the histogram
+            if ((hist && plan && plan->n_pass <= SW_HIST_MAX && !brute) || persist == 1) {
+                // persistent grid: every CTA keeps its digit counters in shared memory over all of its chunks
+                static int occ = 0;
+                if (!occ) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seq_words_kernel<W, Suf, 0, false, 32, 1>, SW_THREADS, 0));
+                int sms = 0;
+                CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device));
+                if (persist) grid = (unsigned)std::min<uint64_t>(b.n_chunks, (uint64_t)sms * (uint64_t)std::max(occ, 1));
+                if (hist && plan && plan->n_pass <= SW_HIST_MAX && !brute) { sa.hist = hist; sa.hist_first = plan->first; sa.hist_np = plan->n_pass; }
+            }
             if (brute) CBL_LAUNCH((seq_words_kernel<W, Suf, 0, true, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
             else CBL_LAUNCH((seq_words_kernel<W, Suf, 0, false, 32, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
         } else {
             CBL_LAUNCH((seq_words_kernel<W, Suf, 1, false, CBL_PROBE_WB, 1>), grid, SW_THREADS, 0, s, b, P_, d_words, d_flags, v, err, sa);
         }
     }
-    // membership of n words (MODE 3 of the fused kernel: same staged probe + deferred queue, no sequence front end);
-    // d_flags may be peer memory
+    // membership of the words of up to PROBE_MAX_SEG device segments in ONE launch (MODE 3 of the fused kernel: same
+    // staged probe + deferred queue, no sequence front end); the answer pointers may be peer memory
+    void launch_probe_segments(const void* const* seg, const uint64_t* seg_n, uint8_t* const* seg_out, uint32_t n_seg, cudaStream_t s) {
+        uint32_t done = 0;
+        while (done < n_seg) {
+            ShardArgs<W> sa{};
+            uint64_t chunks = 0;
+            int k = 0;
+            for (; done < n_seg && k < PROBE_MAX_SEG; done++) {
+                if (seg_n[done] == 0) continue;
+                sa.seg_words[k] = (const W*)seg[done];
+                sa.seg_out[k] = seg_out[done];
+                sa.seg_n[k] = seg_n[done];
+                sa.seg_chunk0[k] = chunks;
+                chunks += div_up(seg_n[done], CHUNK_KMERS);
+                k++;
+            }
+            for (int t = k; t <= PROBE_MAX_SEG; t++) sa.seg_chunk0[t] = chunks;
+            sa.n_seg = k;
+            if (k == 0) continue;
+            // CBL_WORDS_GRID caps the grid (the kernel strides over the chunks)
+            const unsigned grid = (unsigned)std::min<uint64_t>(chunks, env_u64("CBL_WORDS_GRID", 1u << 30));
+            CBL_LAUNCH((seq_words_kernel<W, Suf, 3, false, CBL_PROBE_WB, 1>), grid, SW_THREADS, 0, s, SeqBatch{}, P_, (W*)nullptr, (uint8_t*)nullptr,
+                       view(), (unsigned long long*)nullptr, sa);
+        }
+    }
     void launch_probe_words(const W* d_words, uint64_t n, uint8_t* d_flags, cudaStream_t s) {
-        if (n == 0) return;
-        ShardArgs<W> sa{};
-        sa.in_words = d_words;
-        sa.n_in = n;
-        // CBL_WORDS_GRID / CBL_ROUTE_GRID cap the grids (the kernels stride over the chunks) so that the owner-side probe and
-        // the next sub-batch's route kernel can be co-resident on every SM (sharded pipeline, cbl_b200/sharded.py)
-        const unsigned grid = (unsigned)std::min<uint64_t>(div_up(n, CHUNK_KMERS), env_u64("CBL_WORDS_GRID", 1u << 30));
-        CBL_LAUNCH((seq_words_kernel<W, Suf, 3, false, CBL_PROBE_WB, 1>), grid, SW_THREADS, 0, s, SeqBatch{}, P_, (W*)nullptr, d_flags, view(),
-                   (unsigned long long*)nullptr, sa);
+        const void* seg[1] = {d_words};
+        uint8_t* out[1] = {d_flags};
+        launch_probe_segments(seg, &n, out, 1, s);
     }
     static void throw_bad_byte(unsigned long long e) {
         throw Error(CBL_EINVAL, "non-ACGT byte in sequence near byte offset " + std::to_string(e) +
@@ -317,7 +414,7 @@ public:
         pl.n_chunks = nc;
         out.clean.alloc(bytes + 64, s);
         upload_pieces(pl, 0, nc, 0, out.clean.get(), bytes, out.dp, s);
-        CBL_LAUNCH(sanitize_chunks_kernel, grid, SAN_THREADS, 0, s, in, cfg_.k, (uint32_t*)nullptr, (const uint64_t*)out.dp.byte_off.get(), out.clean.get());
+        CBL_LAUNCH(sanitize_chunks_kernel, grid, SAN_THREADS, 0, s, in, cfg_.k, (uint32_t*)nullptr, out.dp.batch.piece_byte, out.clean.get());
         out.n_kmers = pl.n_kmers;
     }
     // Synchronous.  Returns the number of words / answers written (at the front of d_words / d_flags): the batch's
@@ -342,57 +439,57 @@ public:
     }
 
     // ------------------------------------------------------------------------------------------
-    // sort / unique
+    // batch sort (no host synchronisation inside: the fail flag is read with the mutation's status block)
     // ------------------------------------------------------------------------------------------
-    // sorts n keys; returns the buffer (a or b) that holds the result
-    // Hybrid (default): LSD passes over the top digits only, then the in-shared-memory segment sort (seg_sort.cuh).
-    // The number of passes is chosen so that the largest group of words sharing their sorted top bits fits a segment
-    // tile: for k-mer data the most frequent b-bit head of a necklace word has mass ~ 2K / 2^b.  Any other
-    // distribution is still sorted exactly: a segment that does not fit raises the fail flag and the batch is re-sorted
-    // by the plain LSD passes.  CBL_SORT=lsd selects the plain passes outright.
-    W* sort_keys(W* a, W* b, uint64_t n) {
-        if (n <= 1) return a;
+    // device status block of one mutation, read back once at its end (h_status_ mirrors it)
+    enum { ST_MERGED = 0, ST_BUCKETS = 1, ST_DIR_ELEMS = 2, ST_LAST_PREFIX = 3, ST_SORT_FAIL = 4, ST_BAD_BYTE = 5, ST_WORDS = 8 };
+    void init_status(DevBuf<unsigned long long>& st) {
+        st.alloc(ST_WORDS, st_);
+        CUDA_CHECK(cudaMemsetAsync(st.get(), 0, ST_WORDS * 8, st_));
+        CUDA_CHECK(cudaMemsetAsync(st.get() + ST_BAD_BYTE, 0xFF, 8, st_));
+    }
+    void read_status(const DevBuf<unsigned long long>& st) {   // the ONE synchronisation of a mutation
+        CUDA_CHECK(cudaMemcpyAsync(h_status_, st.get(), ST_WORDS * 8, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    struct Sorted {
+        W* out;        // the sorted words
+        W* grouped;    // hybrid sort: the buffer that still holds every word grouped by its top digits (input of the segment sort)
+    };
+    // sorts n keys held in a (b: same-size scratch).  hist: digit counters of plan's passes already filled by the words
+    // kernel, or null (counted here).  fail: device flag the segment sort raises when a group does not fit its tile.
+    Sorted sort_keys(W* a, W* b, uint64_t n, const SortPlan& sp, unsigned long long* hist, unsigned long long* fail) {
+        if (n <= 1) return {a, a};
         if (n > RS_MAX_KEYS) throw Error(CBL_EINVAL, "internal: sort batch too large");
-        const int key_bits = P_.bits + P_.pos_bits;
-        const int n_digits = (key_bits + 7) / 8;
-        int n_pass = n_digits;
-        const char* sort_env = getenv("CBL_SORT");
-        const bool hybrid = !(sort_env && std::string(sort_env) == "lsd");
-        if (hybrid) {
-            for (int c = 1; c < n_digits - 1; c++) {   // c LSD passes leave 8 * (n_digits - c) low bits to the segment sort
-                const int b = key_bits - 8 * (n_digits - c);
-                const double est = (double)n * (double)P_.bits / std::ldexp(1.0, b);
-                if (est * 1.5 <= (double)SsTile<W>::T) { n_pass = c; break; }
-            }
-        }
-        W* res = lsd_passes(a, b, n, n_digits - n_pass, n_pass);
-        if (n_pass == n_digits) return res;
+        W* res = lsd_passes(a, b, n, sp.first, sp.n_pass, hist);
+        if (sp.n_pass == sp.n_digits) return {res, res};
         W* other = res == a ? b : a;
-        DevBuf<unsigned> fail(1, st_);
-        fail.zero();
-        const int shift = 8 * (n_digits - n_pass);
+        const int key_bits = P_.bits + P_.pos_bits;
+        const int shift = 8 * (sp.n_digits - sp.n_pass);
         // nominal tile: leave room for segments 3x longer than the longest one expected, at least 512 keys
         const double est_seg = (double)n * (double)P_.bits / std::ldexp(1.0, key_bits - shift);
         const int room = (int)std::min<double>(SsTile<W>::CAP / 2, std::max<double>(512.0, std::ceil(3.0 * est_seg / 256.0) * 256.0));
         const int tile = SsTile<W>::CAP - room;
+        unsigned* f = reinterpret_cast<unsigned*>(fail);
         if (shift <= 32)
-            CBL_LAUNCH((seg_sort_kernel<W, true>), (unsigned)div_up(n, (uint64_t)tile), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, fail.get(), tile);
+            CBL_LAUNCH((seg_sort_kernel<W, true>), (unsigned)div_up(n, (uint64_t)tile), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, f, tile);
         else
-            CBL_LAUNCH((seg_sort_kernel<W, false>), (unsigned)div_up(n, (uint64_t)tile), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, fail.get(), tile);
-        unsigned h_fail = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&h_fail, fail.get(), sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
-        CUDA_CHECK(cudaStreamSynchronize(st_));
-        if (!h_fail) return other;
-        g_sort_fallbacks.fetch_add(1, std::memory_order_relaxed);
-        return lsd_passes(res, other, n, 0, n_digits);   // `res` still holds every word (grouped by its top digits)
+            CBL_LAUNCH((seg_sort_kernel<W, false>), (unsigned)div_up(n, (uint64_t)tile), SS_THREADS, SsTile<W>::SMEM, st_, res, other, n, shift, f, tile);
+        return {other, res};
     }
-    // LSD passes over digits [first, first + n_pass); returns the buffer that holds the result
-    W* lsd_passes(W* a, W* b, uint64_t n, int first, int n_pass) {
-        DevBuf<unsigned long long> hist((size_t)n_pass * 256, st_);
-        hist.zero();
-        unsigned hgrid = (unsigned)std::min<uint64_t>(div_up(n, RH_THREADS * RH_KEYS), 148 * 4);
-        CBL_LAUNCH((radix_hist_kernel<W>), hgrid, RH_THREADS, (size_t)n_pass * 256 * sizeof(uint32_t), st_, a, n, n_pass, hist.get(), first);
-        CBL_LAUNCH(radix_scan_hist_kernel, n_pass, 256, 0, st_, hist.get());
+    // LSD passes over digits [first, first + n_pass); returns the buffer that holds the result.  ext_hist: counters of
+    // exactly these digits, already filled (not yet scanned); null: counted here with one more read of the keys.
+    W* lsd_passes(W* a, W* b, uint64_t n, int first, int n_pass, unsigned long long* ext_hist = nullptr) {
+        DevBuf<unsigned long long> own;
+        unsigned long long* hist = ext_hist;
+        if (!hist) {
+            own.alloc((size_t)n_pass * 256, st_);
+            own.zero();
+            hist = own.get();
+            unsigned hgrid = (unsigned)std::min<uint64_t>(div_up(n, RH_THREADS * RH_KEYS), 148 * 4);
+            CBL_LAUNCH((radix_hist_kernel<W>), hgrid, RH_THREADS, (size_t)n_pass * 256 * sizeof(uint32_t), st_, a, n, n_pass, hist, first);
+        }
+        CBL_LAUNCH(radix_scan_hist_kernel, n_pass, 256, 0, st_, hist);
         const uint64_t tiles = div_up(n, RsTile<W>::TILE);
         DevBuf<uint32_t> status(tiles * 256, st_), counter(1, st_);
         const size_t smem = sizeof(W) * RsTile<W>::TILE;
@@ -401,29 +498,14 @@ public:
             status.zero();
             counter.zero();
             CBL_LAUNCH((radix_pass_kernel<W, false, ByteDigit<W>>), (unsigned)tiles, RS_THREADS, smem, st_, src, dst, nullptr, nullptr, n,
-                       ByteDigit<W>{8 * (first + p)}, hist.get() + (size_t)p * 256, status.get(), counter.get(), (uint32_t*)nullptr);
+                       ByteDigit<W>{8 * (first + p)}, hist + (size_t)p * 256, status.get(), counter.get(), (uint32_t*)nullptr);
             std::swap(src, dst);
         }
         return src;
     }
-    uint64_t read_u64(const unsigned long long* d) {
-        unsigned long long v = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, st_));
-        CUDA_CHECK(cudaStreamSynchronize(st_));
-        return v;
-    }
-    uint64_t unique_keys(const W* sorted, uint64_t n, W* out) {
-        if (n == 0) return 0;
-        const uint64_t tiles = div_up(n, OP_TILE);
-        Lookback lb(tiles, st_);
-        DevBuf<unsigned long long> cnt(1, st_);
-        cnt.zero();
-        CBL_LAUNCH((unique_kernel<W>), (unsigned)tiles, OP_THREADS, 0, st_, sorted, n, out, lb.status.get(), lb.counter.get(), cnt.get());
-        return read_u64(cnt.get());
-    }
 
     // ------------------------------------------------------------------------------------------
-    // mutation: sorted distinct probe keys -> edits -> new directory -> new suffix array
+    // new state of the shard after a mutation (built out of place, then swapped in)
     // ------------------------------------------------------------------------------------------
     struct NewState {
         DevBuf<uint2> dir, bucket_range;
@@ -432,7 +514,8 @@ public:
         uint32_t nb = 0;
         uint64_t n = 0;
         uint32_t last_prefix = 0;
-        bool changed = false;
+        bool changed = false;   // a new state was built (its totals still have to be read: finish_new_state)
+        bool pending = false;   // kernels enqueued, totals not read yet
     };
     void adopt(NewState& ns) {
         dir_.swap(ns.dir); bucket_range_.swap(ns.bucket_range); bucket_prefix_.swap(ns.bucket_prefix);
@@ -442,86 +525,8 @@ public:
         dir_.rebind(st_); bucket_range_.rebind(st_); bucket_prefix_.rebind(st_); bucket_off_.rebind(st_); suf_.rebind(st_);
     }
 
-    // keys: sorted distinct words.  probe_ix: index they are looked up in (own view unless KEEP_ONLY).
-    // scratch_ins: optional buffer (>= nk words) reused for the insert list.
-    void compute_new_state(const W* keys, uint64_t nk, int mode, const IndexView<Suf>& probe_ix, W* scratch_ins, NewState& ns) {
-        ns.changed = false;
-        if (nk == 0) return;
-        const IndexView<Suf> self = view();
-        const uint64_t tiles = div_up(nk, OP_TILE);
-        DevBuf<W> ins_own;
-        W* ins_key = scratch_ins;
-        const bool want_ins = (mode & EDIT_INS) != 0;
-        const bool want_del = (mode & (EDIT_DEL | EDIT_KEEP_ONLY)) != 0;
-        if (want_ins && !ins_key) { ins_own.alloc(nk, st_); ins_key = ins_own.get(); }
-        DevBuf<uint64_t> ins_vpos(want_ins ? nk : 1, st_), del_idx(want_del ? nk : 1, st_);
-        DevBuf<int> delta(nb_ ? nb_ : 1, st_);
-        delta.zero();
-        ns.dir.alloc(n_dir_, st_);
-        CUDA_CHECK(cudaMemcpyAsync(ns.dir.get(), dir_.get(), n_dir_ * sizeof(uint2), cudaMemcpyDeviceToDevice, st_));
-        Lookback lb_ins(tiles, st_), lb_del(tiles, st_);
-        DevBuf<unsigned long long> counts(4, st_);
-        counts.zero();
-        CBL_LAUNCH((probe_edits_kernel<W, Suf>), (unsigned)tiles, OP_THREADS, 0, st_, keys, nk, probe_ix, self, P_, mode, ins_key,
-                   ins_vpos.get(), del_idx.get(), delta.get(), ns.dir.get(), lb_ins.status.get(),
-                   lb_del.status.get(), lb_ins.counter.get(), counts.get());
-        unsigned long long h_counts[2] = {0, 0};
-        CUDA_CHECK(cudaMemcpyAsync(h_counts, counts.get(), 16, cudaMemcpyDeviceToHost, st_));
-        CUDA_CHECK(cudaStreamSynchronize(st_));
-        const uint64_t ni = h_counts[0], nd = h_counts[1];
-        if (ni == 0 && nd == 0) return;
-        const uint64_t n_new = n_ + ni - nd;
-        if (n_new >= (1ull << 32))
-            throw Error(CBL_EINVAL, "shard would hold >= 2^32 k-mers; bucket offsets are 32-bit — shard the index over more GPUs");
-
-        // directory
-        if (nb_) CBL_LAUNCH(clear_emptied_kernel, (unsigned)div_up(nb_, 256), 256, 0, st_, bucket_prefix_.get(), bucket_off_.get(),
-                            delta.get(), nb_, ns.dir.get());
-        {
-            const uint64_t t = div_up(n_dir_, OP_TILE);
-            Lookback lb(t, st_);
-            CBL_LAUNCH(rank_directory_kernel, (unsigned)t, OP_THREADS, 0, st_, ns.dir.get(), n_dir_, lb.status.get(), lb.counter.get(),
-                       counts.get() + 2);
-        }
-        const uint64_t nb_new = read_u64(counts.get() + 2);
-        DevBuf<uint32_t> size_new(nb_new + 1, st_);
-        size_new.zero();
-        ns.bucket_prefix.alloc(nb_new ? nb_new : 1, st_);
-        if (nb_) CBL_LAUNCH(fill_sizes_old_kernel, (unsigned)div_up(nb_, 256), 256, 0, st_, bucket_prefix_.get(), bucket_off_.get(),
-                            delta.get(), nb_, ns.dir.get(), size_new.get(), ns.bucket_prefix.get());
-        if (ni) CBL_LAUNCH((fill_sizes_ins_kernel<W>), (unsigned)div_up(ni, 256), 256, 0, st_, ins_key, ni, P_, dir_.get(), ns.dir.get(),
-                           size_new.get(), ns.bucket_prefix.get());
-        ns.bucket_off.alloc(nb_new + 1, st_);
-        ns.bucket_range.alloc(nb_new ? nb_new : 1, st_);
-        {
-            const uint64_t t = div_up(nb_new + 1, OP_TILE);
-            Lookback lb(t, st_);
-            CBL_LAUNCH(scan_sizes_kernel, (unsigned)t, OP_THREADS, 0, st_, size_new.get(), nb_new, ns.bucket_off.get(), ns.bucket_range.get(), lb.status.get(),
-                       lb.counter.get());
-        }
-        // suffixes
-        ns.suf.alloc(n_new + SUF_PAD, st_);
-        {
-            const uint64_t V = n_ + ni;
-            const uint64_t t = div_up(V, OP_TILE);
-            Lookback lb(t, st_);
-            if (t) CBL_LAUNCH((apply_edits_kernel<W, Suf>), (unsigned)t, OP_THREADS, 0, st_, suf_.get(), n_, ins_vpos.get(), ins_key, ni,
-                              del_idx.get(), nd, ns.suf.get(), P_, lb.status.get(), lb.counter.get());
-        }
-        uint32_t tail[2] = {0, 0};  // total from the offsets scan, prefix of the last bucket
-        CUDA_CHECK(cudaMemcpyAsync(&tail[0], ns.bucket_off.get() + nb_new, 4, cudaMemcpyDeviceToHost, st_));
-        if (nb_new) CUDA_CHECK(cudaMemcpyAsync(&tail[1], ns.bucket_prefix.get() + (nb_new - 1), 4, cudaMemcpyDeviceToHost, st_));
-        CUDA_CHECK(cudaStreamSynchronize(st_));
-        if ((uint64_t)tail[0] != n_new)
-            throw Error(CBL_ECUDA, "internal: directory total " + std::to_string(tail[0]) + " != element count " + std::to_string(n_new));
-        ns.nb = (uint32_t)nb_new;
-        ns.n = n_new;
-        ns.last_prefix = tail[1];
-        ns.changed = true;
-    }
-
     // ------------------------------------------------------------------------------------------
-    // mutation by one streaming merge (merge_ops.cuh): keys = sorted distinct words, op = MERGE_*
+    // mutation by one streaming merge (merge_ops.cuh): B = sorted words (repeats allowed) or another index (CSR)
     // ------------------------------------------------------------------------------------------
     static uint64_t round_capacity(uint64_t n) {
         if (n < (1u << 20)) return n;
@@ -529,17 +534,34 @@ public:
         const uint64_t step = 1ull << (top - 2);
         return (n + step - 1) / step * step;
     }
-    template <int OP> void launch_merge_apply(unsigned tiles, const IndexView<Suf>& v, const W* keys, uint64_t nk, const uint32_t* part_i,
-                                              const uint32_t* part_r, Suf* suf_out, uint32_t* cnt, uint64_t* status, uint32_t* counter,
-                                              unsigned long long* n_out) {
+    template <bool BCSR> void launch_merge_apply(int op, unsigned tiles, const IndexView<Suf>& v, const MergeB<W, Suf, BCSR>& B, const uint32_t* part_i,
+                                                 const uint32_t* part_r, const uint32_t* part_rb, Suf* suf_out, uint32_t* cnt, uint64_t* status,
+                                                 uint32_t* counter, unsigned long long* n_out, const unsigned long long* skip) {
         const size_t smem = (size_t)MG_SMEM_ELEMS * sizeof(W);
-        CBL_LAUNCH((merge_apply_kernel<W, Suf, OP>), tiles, MG_THREADS, smem, st_, v, P_, keys, nk, part_i, part_r, suf_out, cnt, status,
-                   counter, n_out);
+#define CBL_MERGE_CASE(OP) \
+    CBL_LAUNCH((merge_apply_kernel<W, Suf, OP, BCSR>), tiles, MG_THREADS, smem, st_, v, P_, B, part_i, part_r, part_rb, suf_out, cnt, status, counter, n_out, skip)
+        if constexpr (BCSR) {
+            switch (op) {
+                case MERGE_OR: CBL_MERGE_CASE(MERGE_OR); break;
+                case MERGE_AND: CBL_MERGE_CASE(MERGE_AND); break;
+                case MERGE_SUB: CBL_MERGE_CASE(MERGE_SUB); break;
+                default: CBL_MERGE_CASE(MERGE_XOR); break;
+            }
+        } else {   // batches only insert or remove
+            if (op == MERGE_OR) CBL_MERGE_CASE(MERGE_OR);
+            else if (op == MERGE_SUB) CBL_MERGE_CASE(MERGE_SUB);
+            else throw Error(CBL_EINVAL, "internal: word batches support insert / remove only");
+        }
+#undef CBL_MERGE_CASE
     }
-    void merge_new_state(const W* keys, uint64_t nk, int op, NewState& ns) {
+    // Enqueues the whole mutation (partition, merge, directory, bucket tables) on the handle's stream and returns without
+    // waiting: the totals land in dstat (ST_MERGED .. ST_LAST_PREFIX).  finish_new_state() turns them into ns.n / ns.nb
+    // after the caller's read_status().
+    template <bool BCSR> void merge_new_state(const MergeB<W, Suf, BCSR>& B, uint64_t nB, int op, NewState& ns, unsigned long long* dstat) {
         ns.changed = false;
-        const uint64_t V = n_ + nk;
-        if (nk == 0 || (n_ == 0 && (op == MERGE_AND || op == MERGE_SUB))) {
+        ns.pending = false;
+        const uint64_t V = n_ + nB;
+        if (nB == 0 || (n_ == 0 && (op == MERGE_AND || op == MERGE_SUB))) {
             if (op == MERGE_AND && n_ != 0) {  // A & {} = {}
                 ns.dir.alloc(n_dir_, st_); ns.dir.zero();
                 ns.bucket_range.alloc(1, st_); ns.bucket_prefix.alloc(1, st_); ns.bucket_off.alloc(1, st_); ns.bucket_off.zero();
@@ -550,25 +572,20 @@ public:
         }
         const IndexView<Suf> v = view();
         const uint64_t tiles = div_up(V, MG_TILE);
-        DevBuf<uint32_t> part_i(tiles + 1, st_), part_r(tiles + 1, st_);
-        CBL_LAUNCH((merge_partition_kernel<W, Suf>), (unsigned)div_up(tiles + 1, 128), 128, 0, st_, v, P_, keys, nk, tiles, part_i.get(), part_r.get());
+        DevBuf<uint32_t> part_i(tiles + 1, st_), part_r(tiles + 1, st_), part_rb(BCSR ? tiles + 1 : 1, st_);
+        CBL_LAUNCH((merge_partition_kernel<W, Suf, BCSR>), (unsigned)div_up(tiles + 1, 128), 128, 0, st_, v, P_, B, tiles, part_i.get(), part_r.get(), part_rb.get(),
+                   (const unsigned long long*)(dstat + ST_SORT_FAIL));
         const uint64_t n_prefix = n_dir_ * 32;
         DevBuf<uint32_t> cnt(n_prefix, st_);
         cnt.zero();
         // capacity is rounded up to 4 steps per octave so that the blocks freed by earlier, smaller states of a
-        // growing index can be reused by the memory pool instead of a fresh driver allocation per batch
-        const uint64_t cap = round_capacity((op == MERGE_AND || op == MERGE_SUB) ? n_ : V);
-        ns.suf.alloc(cap + SUF_PAD, st_);
-        DevBuf<unsigned long long> totals(4, st_);
-        totals.zero();
+        // growing index can be reused by the arena instead of a fresh driver allocation per batch
+        const uint64_t out_max = (op == MERGE_AND || op == MERGE_SUB) ? n_ : V;
+        ns.suf.alloc(round_capacity(out_max) + SUF_PAD, st_);
         {
             Lookback lb(tiles, st_);
-            switch (op) {
-                case MERGE_OR: launch_merge_apply<MERGE_OR>((unsigned)tiles, v, keys, nk, part_i.get(), part_r.get(), ns.suf.get(), cnt.get(), lb.status.get(), lb.counter.get(), totals.get()); break;
-                case MERGE_AND: launch_merge_apply<MERGE_AND>((unsigned)tiles, v, keys, nk, part_i.get(), part_r.get(), ns.suf.get(), cnt.get(), lb.status.get(), lb.counter.get(), totals.get()); break;
-                case MERGE_SUB: launch_merge_apply<MERGE_SUB>((unsigned)tiles, v, keys, nk, part_i.get(), part_r.get(), ns.suf.get(), cnt.get(), lb.status.get(), lb.counter.get(), totals.get()); break;
-                default: launch_merge_apply<MERGE_XOR>((unsigned)tiles, v, keys, nk, part_i.get(), part_r.get(), ns.suf.get(), cnt.get(), lb.status.get(), lb.counter.get(), totals.get()); break;
-            }
+            launch_merge_apply<BCSR>(op, (unsigned)tiles, v, B, part_i.get(), part_r.get(), part_rb.get(), ns.suf.get(), cnt.get(), lb.status.get(),
+                                     lb.counter.get(), dstat + ST_MERGED, dstat + ST_SORT_FAIL);
         }
         ns.dir.alloc(n_dir_, st_);
         DevBuf<uint32_t> word_off(n_dir_, st_);
@@ -576,54 +593,71 @@ public:
             const uint64_t t = div_up(n_dir_, 256);
             Lookback lb_rank(t, st_), lb_off(t, st_);
             CBL_LAUNCH(dir_bits_kernel, (unsigned)t, 256, 0, st_, cnt.get(), n_dir_, ns.dir.get(), word_off.get(), lb_rank.status.get(),
-                       lb_off.status.get(), lb_rank.counter.get(), totals.get() + 1);
+                       lb_off.status.get(), lb_rank.counter.get(), dstat + ST_BUCKETS);
         }
-        unsigned long long h[3] = {0, 0, 0};  // merged element count, buckets, elements by the directory
-        CUDA_CHECK(cudaMemcpyAsync(h, totals.get(), sizeof h, cudaMemcpyDeviceToHost, st_));
-        CUDA_CHECK(cudaStreamSynchronize(st_));
-        const uint64_t n_new = h[0], nb_new = h[1];
-        if (h[2] != n_new)
-            throw Error(CBL_ECUDA, "internal: directory total " + std::to_string(h[2]) + " != element count " + std::to_string(n_new));
+        // the bucket tables are sized by an upper bound (the bucket count is still on the device)
+        const uint64_t nb_max = std::max<uint64_t>(1, std::min<uint64_t>(n_prefix, out_max));
+        ns.bucket_prefix.alloc(nb_max, st_);
+        ns.bucket_off.alloc(nb_max + 1, st_);
+        ns.bucket_range.alloc(nb_max, st_);
+        CBL_LAUNCH(dir_fill_kernel, (unsigned)div_up(n_dir_, 256), 256, 0, st_, cnt.get(), ns.dir.get(), word_off.get(), n_dir_,
+                   ns.bucket_prefix.get(), ns.bucket_off.get(), ns.bucket_range.get(), dstat);
+        ns.changed = true;
+        ns.pending = true;
+    }
+    void finish_new_state(NewState& ns) {   // after read_status()
+        if (!ns.pending) return;
+        const uint64_t n_new = h_status_[ST_MERGED], nb_new = h_status_[ST_BUCKETS];
+        if (h_status_[ST_DIR_ELEMS] != n_new)
+            throw Error(CBL_ECUDA, "internal: directory total " + std::to_string(h_status_[ST_DIR_ELEMS]) + " != element count " + std::to_string(n_new));
         if (n_new >= (1ull << 32))
             throw Error(CBL_EINVAL, "shard would hold >= 2^32 k-mers; bucket offsets are 32-bit — shard the index over more GPUs");
-        ns.bucket_prefix.alloc(nb_new ? nb_new : 1, st_);
-        ns.bucket_off.alloc(nb_new + 1, st_);
-        ns.bucket_range.alloc(nb_new ? nb_new : 1, st_);
-        CBL_LAUNCH(dir_fill_kernel, (unsigned)div_up(n_dir_, 256), 256, 0, st_, cnt.get(), ns.dir.get(), word_off.get(), n_dir_,
-                   ns.bucket_prefix.get(), ns.bucket_off.get(), ns.bucket_range.get(), (uint32_t)nb_new, (uint32_t)n_new);
-        uint32_t last = 0;
-        if (nb_new) CUDA_CHECK(cudaMemcpyAsync(&last, ns.bucket_prefix.get() + (nb_new - 1), 4, cudaMemcpyDeviceToHost, st_));
-        CUDA_CHECK(cudaStreamSynchronize(st_));
         ns.nb = (uint32_t)nb_new;
         ns.n = n_new;
-        ns.last_prefix = last;
-        ns.changed = true;
+        ns.last_prefix = nb_new ? (uint32_t)h_status_[ST_LAST_PREFIX] : 0;
+        ns.pending = false;
     }
 
-    // unsorted words in `a` (n of them, `b` same-size scratch) -> applied to this index
-    void mutate_with_words(W* a, W* b, uint64_t n, int mode) {
-        if (n == 0) return;
+    // unsorted words in `a` (n of them, `b` same-size scratch) -> applied to this index.  hist (optional): digit counters
+    // of plan_sort(n)'s passes already filled by the kernel that produced the words; dstat (optional): the caller's status
+    // block (then the caller has initialised it and ST_BAD_BYTE is meaningful).  Returns false when the words kernel
+    // reported a non-ACGT byte (nothing was applied; the caller re-runs the batch through the sanitiser).
+    bool mutate_with_words(W* a, W* b, uint64_t n, int mode, unsigned long long* hist = nullptr, DevBuf<unsigned long long>* ext_stat = nullptr) {
+        if (n == 0) return true;
         Trace tr(st_);
-        W* sorted = sort_keys(a, b, n);
-        tr.mark("  sort enqueue");
+        const int op = mode == EDIT_INS ? MERGE_OR : MERGE_SUB;
+        const SortPlan sp = plan_sort(n);
+        DevBuf<unsigned long long> own_stat;
+        if (!ext_stat) init_status(own_stat);
+        DevBuf<unsigned long long>& stat = ext_stat ? *ext_stat : own_stat;
+        Sorted so = sort_keys(a, b, n, sp, hist, stat.get() + ST_SORT_FAIL);
         NewState ns;
-        if (use_merge_) {
-            // the merge treats a repeated batch word as one (merge_ops.cuh): no unique pass, no count read-back
-            merge_new_state(sorted, n, mode == EDIT_INS ? MERGE_OR : MERGE_SUB, ns);
-        } else {
-            W* other = sorted == a ? b : a;
-            uint64_t nu = unique_keys(sorted, n, other);
-            tr.mark("  unique (sync inside)");
-            compute_new_state(other, nu, mode, view(), sorted, ns);
+        // the merge treats a repeated batch word as one (merge_ops.cuh): no unique pass, no count read-back
+        merge_new_state<false>(MergeB<W, Suf, false>{so.out, n}, n, op, ns, stat.get());
+        tr.mark("  sort + merge enqueued");
+        read_status(stat);
+        tr.mark("  status read (the one sync)");
+        if (h_status_[ST_BAD_BYTE] != ULLONG_MAX) return false;
+        if (h_status_[ST_SORT_FAIL]) {   // a group of equal top digits did not fit a segment tile: plain LSD passes (exact for any input)
+            g_sort_fallbacks.fetch_add(1, std::memory_order_relaxed);
+            W* other = so.grouped == a ? b : a;
+            W* sorted = lsd_passes(so.grouped, other, n, 0, sp.n_digits);
+            init_status(stat);
+            ns = NewState();
+            merge_new_state<false>(MergeB<W, Suf, false>{sorted, n}, n, op, ns, stat.get());
+            read_status(stat);
         }
-        tr.mark("  new state (syncs inside)");
+        finish_new_state(ns);
         if (ns.changed) adopt(ns);
         tr.mark("  adopt");
+        return true;
     }
 
     // ------------------------------------------------------------------------------------------
     // sequence front ends
     // ------------------------------------------------------------------------------------------
+    // One batch = words kernel (with the sort's digit histograms folded in) -> LSD passes -> segment sort -> merge ->
+    // directory, all enqueued back to back; the host waits once, at the end, for the status block.
     void mutate_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, int mode) {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         check_records(offsets, n_seqs);
@@ -639,14 +673,24 @@ public:
             Trace tr(st_);
             DevPieces dp;
             upload_pieces(pl, p, q, pl.out_off[p], d_seq, n_bytes, dp, st_);
-            tr.mark("upload pieces");
             DevBuf<W> a(nk, st_), b(nk, st_);
-            tr.mark("alloc a,b");
-            const uint64_t produced = run_seq_words(dp.batch, nk, 0, false, a.get(), nullptr, st_);
+            tr.mark("upload pieces, alloc a,b");
+            const SortPlan sp = plan_sort(nk);
+            DevBuf<unsigned long long> stat, hist;
+            init_status(stat);
+            const bool fused_hist = sp.n_pass <= SW_HIST_MAX && nk > 1 && env_u64("CBL_HIST_FUSED", 1) != 0;
+            if (fused_hist) { hist.alloc((size_t)sp.n_pass * 256, st_); hist.zero(); }
+            launch_seq_words(dp.batch, 0, false, a.get(), nullptr, stat.get() + ST_BAD_BYTE, st_, fused_hist ? hist.get() : nullptr, &sp);
+            uint64_t produced = nk;
+            if (!mutate_with_words(a.get(), b.get(), nk, mode, fused_hist ? hist.get() : nullptr, &stat)) {
+                // non-ACGT bytes: nothing was applied; the sanitised reads take the plain path
+                Sanitized sn;
+                sanitize_batch(dp.batch, sn, st_);
+                produced = run_seq_words(sn.dp.batch, sn.n_kmers, 0, false, a.get(), nullptr, st_);
+                mutate_with_words(a.get(), b.get(), produced, mode);
+            }
             last_produced += produced;
-            tr.mark("seq_words (sync inside)");
-            mutate_with_words(a.get(), b.get(), produced, mode);
-            tr.mark("mutate_with_words", true);
+            tr.mark("batch", true);
             p = q;
         }
         CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -913,6 +957,12 @@ public:
             remaining -= m;
         }
     }
+    // membership of the words of n_seg device segments, answers to seg_out[i] (may be peer memory): one launch
+    void words_contains_segments_dev(const void* const* seg, const uint64_t* seg_n, uint8_t* const* seg_out, uint32_t n_seg) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        ensure_sub();
+        launch_probe_segments(seg, seg_n, seg_out, n_seg, st_);
+    }
     void kmers_op(int op, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         if (n == 0) return;
@@ -930,7 +980,14 @@ public:
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         if (n == 0) return;
         std::vector<W> h(n);
-        for (uint64_t i = 0; i < n; i++) h[i] = sizeof(W) == 16 ? (W)(((u128)(hi ? hi[i] : 0) << 64) | lo[i]) : (W)lo[i];
+        const int key_bits = P_.bits + P_.pos_bits;
+        for (uint64_t i = 0; i < n; i++) {
+            h[i] = sizeof(W) == 16 ? (W)(((u128)(hi ? hi[i] : 0) << 64) | lo[i]) : (W)lo[i];
+            // foreign words (a file): a word wider than the key, or the all-ones word (the merge's exhausted-side sentinel;
+            // no k-mer maps to it: the position of an all-ones necklace is 0), cannot come from a k-mer
+            const bool too_wide = key_bits < (int)(8 * sizeof(W)) && (h[i] >> key_bits) != 0;
+            if (too_wide || h[i] == ~(W)0) throw Error(CBL_EINVAL, "word " + std::to_string(i) + " is not the word of a k-mer (wider than 2K + POS_BITS bits, or all ones)");
+        }
         DevBuf<W> d(n, st_);
         CUDA_CHECK(cudaMemcpyAsync(d.get(), h.data(), n * sizeof(W), cudaMemcpyHostToDevice, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -1094,28 +1151,15 @@ public:
         if (c.device != cfg_.device) throw Error(CBL_EINVAL, "set operation between indexes on different devices");
         return p;
     }
+    // A op= B as ONE streaming merge of the two CSR indexes (operand B is never expanded into words); synchronous.
     void setop_new_state(int op, Index* o, NewState& ns) {
         o->sync();
-        if (use_merge_) {
-            if (o->n_ == 0 && op != SETOP_AND) { ns.changed = false; return; }
-            DevBuf<W> theirs(o->n_ ? o->n_ : 1, st_);
-            if (o->n_) CBL_LAUNCH((expand_kernel<W, Suf>), (unsigned)div_up(o->n_, OP_TILE), OP_THREADS, 0, st_, o->view(), P_, (uint64_t)0, o->n_, 0, theirs.get());
-            merge_new_state(theirs.get(), o->n_, op, ns);
-            return;
-        }
-        if (op == SETOP_AND) {
-            if (n_ == 0) { ns.changed = false; return; }
-            DevBuf<W> mine(n_, st_);
-            export_words_dev(0, n_, 0, mine.get());
-            compute_new_state(mine.get(), n_, EDIT_KEEP_ONLY, o->view(), nullptr, ns);
-        } else {
-            if (o->n_ == 0) { ns.changed = false; return; }
-            DevBuf<W> theirs(o->n_, st_);
-            // expand the other operand on OUR stream (its state is final after o->sync())
-            CBL_LAUNCH((expand_kernel<W, Suf>), (unsigned)div_up(o->n_, OP_TILE), OP_THREADS, 0, st_, o->view(), P_, (uint64_t)0, o->n_, 0, theirs.get());
-            const int mode = op == SETOP_OR ? EDIT_INS : op == SETOP_SUB ? EDIT_DEL : (EDIT_INS | EDIT_DEL);
-            compute_new_state(theirs.get(), o->n_, mode, view(), nullptr, ns);
-        }
+        ns.changed = false;
+        if (o->n_ == 0 && op != SETOP_AND) return;
+        DevBuf<unsigned long long> stat;
+        init_status(stat);
+        merge_new_state<true>(MergeB<W, Suf, true>{o->view()}, o->n_, op, ns, stat.get());
+        if (ns.pending) { read_status(stat); finish_new_state(ns); }
     }
     void setop_assign(int op, IIndex* other) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));

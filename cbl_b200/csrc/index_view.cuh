@@ -59,6 +59,15 @@ __device__ __forceinline__ int ldg_keep(const int8_t* p) {
     return (int)__ldg(p);
 #endif
 }
+__device__ __forceinline__ uint32_t ldg_keep(const uint32_t* p) {
+#if CBL_L2_POLICY
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint" CBL_L2_FETCH_Q ".u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_keep()));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 #if CBL_L2_POLICY
     uint4 v;
@@ -126,12 +135,33 @@ template <> __device__ __forceinline__ void unpack16<uint64_t>(const uint4& x, u
 template <> __device__ __forceinline__ void unpack16<u128>(const uint4& x, u128* e) {
     e[0] = ((u128)(((uint64_t)x.w << 32) | x.z) << 64) | (u128)(((uint64_t)x.y << 32) | x.x);
 }
+// one 32-byte load instruction (LDG.256, sm_100): measured on B200 (scripts/ubench/gather_bench.cu) a random 32-byte
+// window costs the memory system the same whether it is fetched by one 16-byte request or one 32-byte request, so
+// two 16-byte loads per window halve the look-up rate (24 vs 48 G windows/s)
+#ifndef CBL_WINDOW_LD256
+#define CBL_WINDOW_LD256 1
+#endif
+__device__ __forceinline__ void ldg_stream256(const void* p, uint4& a, uint4& b) {
+#if CBL_L2_POLICY
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint" CBL_L2_FETCH_Q ".v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p), "l"(l2_policy_stream()));
+#else
+    asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+#endif
+}
 template <class Suf, int WB> __device__ __forceinline__ void load_window(const Suf* __restrict__ p, Suf (&e)[Window<Suf, WB>::N]) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
     constexpr int EPC = 16 / (int)sizeof(Suf);
     uint4 x[WB / 16];
+#if CBL_WINDOW_LD256
+    if (WB == 32) ldg_stream256(q, x[0], x[WB / 16 - 1]);
+    else
+#endif
+    {
 #pragma unroll
-    for (int c = 0; c < WB / 16; c++) x[c] = ldg_stream(q + c);
+        for (int c = 0; c < WB / 16; c++) x[c] = ldg_stream(q + c);
+    }
 #pragma unroll
     for (int c = 0; c < WB / 16; c++) unpack16<Suf>(x[c], &e[c * EPC]);
 }
@@ -225,6 +255,9 @@ __device__ __forceinline__ ProbeResult probe_key(const IndexView<Suf>& ix, const
 #ifndef CBL_SUB_SHIFT
 #define CBL_SUB_SHIFT 4
 #endif
+#ifndef CBL_SUB_ONE_LOAD
+#define CBL_SUB_ONE_LOAD 0
+#endif
 constexpr int SUB_SHIFT = CBL_SUB_SHIFT;
 constexpr int SUB_GROUP = 1 << SUB_SHIFT;
 
@@ -249,8 +282,20 @@ __device__ __forceinline__ uint32_t predict_slot(const int8_t* __restrict__ sub,
     const uint64_t t = (uint64_t)k32 << ss.eb;
     const uint32_t j = (uint32_t)(t >> 32);
     const int frac = (int)((uint32_t)t >> 24);
+#if CBL_SUB_ONE_LOAD
+    // both correction bytes from ONE aligned 4-byte load (a second one only when they straddle a word: 1 lane in 4)
+    const uint32_t bi = ss.first + j;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sub);
+    const uint32_t w0 = ldg_keep(sw + (bi >> 2));
+    uint32_t w1 = 0;
+    if ((bi & 3u) == 3u) w1 = ldg_keep(sw + (bi >> 2) + 1);
+    const uint32_t two = __funnelshift_r(w0, w1, (bi & 3u) * 8);
+    const int d0 = (int)(int8_t)(two & 0xFFu);
+    int d1 = (int)(int8_t)((two >> 8) & 0xFFu);
+#else
     const int d0 = ldg_keep(sub + ss.first + j);
     int d1 = ldg_keep(sub + ss.first + j + 1);
+#endif
     d1 = (j + 1 < (1u << ss.eb)) ? d1 : 0;
     const int corr = ss.eb > 0 ? d0 + (((d1 - d0) * frac + 128) >> 8) : 0;
     const int guess = (int)__umulhi(k32, span) + corr;

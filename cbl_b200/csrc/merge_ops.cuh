@@ -2,7 +2,8 @@
 // streaming merge of two ascending word sequences:
 //     A = the resident index (CSR: prefix of the bucket, suffix of the element), never materialised as words
 //     B = the batch (sorted words, duplicates allowed: a repeated word counts once, so the sort needs no
-//         separate unique pass; for set operations the other index expanded)
+//         separate unique pass) or, for set operations, the OTHER index, read as CSR too (BCSR: no expansion
+//         of the operand into words, traffic N_b * S instead of N_b * (S + 2 W))
 // Replaces WordSet::insert_batch / remove_batch (src/wordset/mod.rs:187-237) and the binary set
 // operations (src/wordset/set_ops.rs:78-410, src/trievec/set_ops.rs:5-257, src/bitvector/set_ops.rs:4-106).
 //
@@ -45,22 +46,80 @@ __device__ __forceinline__ bool index_elem_le(const IndexView<Suf>& ix, const KP
     return ix.suf[i] <= s;
 }
 
+// The B side of a merge: a sorted word array (batch) or a second index in CSR form (set operations).
+template <class W, class Suf, bool BCSR> struct MergeB;
+template <class W, class Suf> struct MergeB<W, Suf, false> {
+    const W* words;
+    uint64_t n;
+    __device__ __forceinline__ uint64_t size() const { return n; }
+    __device__ __forceinline__ W at(uint64_t j, const KParams&) const { return words[j]; }
+    __device__ __forceinline__ uint32_t rank_of(uint64_t) const { return 0; }
+};
+template <class W, class Suf> struct MergeB<W, Suf, true> {
+    IndexView<Suf> ix;
+    __device__ __forceinline__ uint64_t size() const { return ix.n; }
+    __device__ __forceinline__ uint32_t rank_of(uint64_t j) const {   // bucket holding element j (nb when j == n)
+        return j < ix.n ? (uint32_t)(upper_bound_dev<uint32_t>(ix.bucket_off, (uint64_t)ix.nb + 1, (uint32_t)j) - 1) : ix.nb;
+    }
+    __device__ __forceinline__ W at(uint64_t j, const KParams& P) const {
+        const uint32_t r = rank_of(j);
+        return (W)(((W)ix.bucket_prefix[r] << P.suffix_bits) | (W)ix.suf[j]);
+    }
+};
+
 // part_i[t] = number of A elements among the first min(t * TILE, nA + nB) merged elements (A first on
-// ties); part_r[t] = rank of the bucket holding A[part_i[t]] (nb when part_i[t] == nA).  t in [0, tiles].
-template <class W, class Suf>
-__global__ void merge_partition_kernel(IndexView<Suf> ix, KParams P, const W* __restrict__ B, uint64_t nB, uint64_t tiles,
-                                       uint32_t* __restrict__ part_i, uint32_t* __restrict__ part_r) {
+// ties); part_r[t] = rank of the bucket holding A[part_i[t]] (nb when part_i[t] == nA); part_rb[t] (BCSR only) = the
+// same for B[t * TILE - part_i[t]].  t in [0, tiles].
+template <class W, class Suf, bool BCSR>
+__global__ void merge_partition_kernel(IndexView<Suf> ix, KParams P, MergeB<W, Suf, BCSR> B, uint64_t tiles,
+                                       uint32_t* __restrict__ part_i, uint32_t* __restrict__ part_r, uint32_t* __restrict__ part_rb,
+                                       const unsigned long long* __restrict__ skip) {
+    // skip: device flag raised by the batch sort when B could NOT be sorted (seg_sort.cuh); merging an unsorted B would
+    // index shared memory out of bounds, and the host re-sorts and re-merges anyway once it has read the flag
+    if (skip && *skip) return;
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > tiles) return;
-    const uint64_t nA = ix.n;
+    const uint64_t nA = ix.n, nB = B.size();
     const uint64_t D = min(t * (uint64_t)MG_TILE, nA + nB);
     uint64_t lo = D > nB ? D - nB : 0, hi = min(D, nA);
     while (lo < hi) {
         const uint64_t mid = (lo + hi) >> 1;
-        if (index_elem_le<W, Suf>(ix, P, (uint32_t)mid, B[D - 1 - mid])) lo = mid + 1; else hi = mid;
+        if (index_elem_le<W, Suf>(ix, P, (uint32_t)mid, B.at(D - 1 - mid, P))) lo = mid + 1; else hi = mid;
     }
     part_i[t] = (uint32_t)lo;
     part_r[t] = lo < nA ? (uint32_t)(upper_bound_dev<uint32_t>(ix.bucket_off, (uint64_t)ix.nb + 1, (uint32_t)lo) - 1) : ix.nb;
+    if (BCSR) part_rb[t] = B.rank_of(D - lo);
+}
+
+// stage elements [i0, i0 + n) of a CSR index as words into dst[0, n): r0 / r1 = bucket ranks of elements i0 and i0 + n
+// (nb past the end).  Uses s_pos / s_pfx as scratch (bucket starts inside the range); block-wide, ends with a barrier.
+template <class W, class Suf>
+__device__ __forceinline__ void stage_csr_words(const IndexView<Suf>& ix, const KParams& P, uint32_t i0, int n, uint32_t r0, uint32_t r1, W* dst,
+                                                uint16_t* s_pos, uint32_t* s_pfx) {
+    int n_bk = 0;
+    if (n > 0) {
+        const uint32_t r_hi = min(r1, ix.nb - 1);             // last candidate rank
+        n_bk = (int)(r_hi - r0) + 1;
+        if (r_hi > r0 && ix.bucket_off[r_hi] >= i0 + (uint32_t)n) n_bk--;   // the bucket of element i0 + n starts exactly there
+        for (int j = threadIdx.x; j < n_bk; j += MG_THREADS) {
+            s_pos[j] = j == 0 ? 0 : (uint16_t)(ix.bucket_off[r0 + j] - i0);
+            s_pfx[j] = ix.bucket_prefix[r0 + j];
+        }
+    }
+    __syncthreads();
+    int lo = 0;                                            // last bucket with start <= s; s grows, so lo never moves back
+    for (int s = threadIdx.x; s < n; s += MG_THREADS) {
+        if (lo + 1 < n_bk && (int)s_pos[lo + 1] <= s) {    // usually false: 256 elements rarely leave a bucket
+            int hi = n_bk;
+            lo++;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int)s_pos[mid] <= s) lo = mid; else hi = mid;
+            }
+        }
+        dst[s] = (W)(((W)s_pfx[lo] << P.suffix_bits) | (W)ix.suf[i0 + s]);
+    }
+    __syncthreads();
 }
 
 // shared-memory slot of output element k: one pad word per 32 elements makes the "8 consecutive elements
@@ -68,12 +127,15 @@ __global__ void merge_partition_kernel(IndexView<Suf> ix, KParams P, const W* __
 __device__ __forceinline__ uint32_t mg_pad(uint32_t k) { return k + (k >> 5); }
 constexpr int MG_SMEM_ELEMS = MG_TILE + 2 + MG_TILE / 32 + 2;   // staging words (also holds the padded output)
 
-template <class W, class Suf, int OP>
-__global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> ix, KParams P, const W* __restrict__ B, uint64_t nB,
+template <class W, class Suf, int OP, bool BCSR>
+__global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> ix, KParams P, MergeB<W, Suf, BCSR> B,
                                                                  const uint32_t* __restrict__ part_i, const uint32_t* __restrict__ part_r,
+                                                                 const uint32_t* __restrict__ part_rb,
                                                                  Suf* __restrict__ suf_out, uint32_t* __restrict__ prefix_cnt,
                                                                  volatile uint64_t* status, uint32_t* tile_counter,
-                                                                 unsigned long long* __restrict__ n_out) {
+                                                                 unsigned long long* __restrict__ n_out,
+                                                                 const unsigned long long* __restrict__ skip) {
+    if (skip && *skip) return;   // see merge_partition_kernel (block-uniform: every tile leaves, nobody waits in the look-back)
     extern __shared__ __align__(16) unsigned char mg_smem[];
     W* sK = reinterpret_cast<W*>(mg_smem);                 // [0] A halo, [1, na] A, (na, na + nb] B, [na + nb + 1] B halo
     Suf* s_out = reinterpret_cast<Suf*>(mg_smem);          // after the merge: emitted suffixes (padded slots)
@@ -84,45 +146,26 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     __shared__ uint64_t s_excl;
     __shared__ uint32_t s_tmp[33];
     __shared__ W s_bprev;                                   // B[j0 - 1]: a B element equal to its predecessor is a repeat
-    const W SENTINEL = ~(W)0;  // no word is all ones (the position field of an all-ones necklace is 0)
+    // Exhausted sides compare as SENTINEL.  No k-mer word is all ones (the position field of an all-ones necklace is
+    // 0); the word-level entry points that accept foreign words reject it (Index::check_foreign_words).
+    const W SENTINEL = ~(W)0;
     constexpr uint32_t NONE = 0xFFFFFFFFu;
 
     const uint32_t tile = block_ticket(tile_counter, &s_tile);
-    const uint64_t nA = ix.n;
+    const uint64_t nA = ix.n, nB = B.size();
     const uint64_t D0 = min((uint64_t)tile * MG_TILE, nA + nB), D1 = min((uint64_t)(tile + 1) * MG_TILE, nA + nB);
     const uint32_t i0 = part_i[tile], i1 = part_i[tile + 1];
     const uint64_t j0 = D0 - i0, j1 = D1 - i1;
     const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
     const uint32_t r0 = part_r[tile], r1 = part_r[tile + 1];
 
-    // ---- buckets of the A range: entry 0 = the bucket holding A[i0], then every bucket starting inside (i0, i1) ----
-    int n_bk = 0;
-    if (na > 0) {
-        const uint32_t r_hi = min(r1, ix.nb - 1);             // last candidate rank
-        n_bk = (int)(r_hi - r0) + 1;
-        if (r_hi > r0 && ix.bucket_off[r_hi] >= i1) n_bk--;   // the bucket of A[i1] starts exactly at i1
-        for (int j = threadIdx.x; j < n_bk; j += MG_THREADS) {
-            s_pos[j] = j == 0 ? 0 : (uint16_t)(ix.bucket_off[r0 + j] - i0);
-            s_pfx[j] = ix.bucket_prefix[r0 + j];
-        }
-    }
-    __syncthreads();
     // ---- stage A words and B words (coalesced global reads, consecutive shared slots) ----
-    {
-        int lo = 0;                                            // last bucket with start <= s; s grows, so lo never moves back
-        for (int s = threadIdx.x; s < na; s += MG_THREADS) {
-            if (lo + 1 < n_bk && (int)s_pos[lo + 1] <= s) {    // usually false: 256 elements rarely leave a bucket
-                int hi = n_bk;
-                lo++;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if ((int)s_pos[mid] <= s) lo = mid; else hi = mid;
-                }
-            }
-            sK[1 + s] = (W)(((W)s_pfx[lo] << P.suffix_bits) | (W)ix.suf[i0 + s]);
-        }
+    stage_csr_words<W, Suf>(ix, P, i0, na, r0, r1, sK + 1, s_pos, s_pfx);
+    if constexpr (BCSR) {
+        stage_csr_words<W, Suf>(B.ix, P, (uint32_t)j0, nb, part_rb[tile], part_rb[tile + 1], sK + 1 + na, s_pos, s_pfx);
+    } else {
+        for (int s = threadIdx.x; s < nb; s += MG_THREADS) sK[1 + na + s] = B.words[j0 + s];
     }
-    for (int s = threadIdx.x; s < nb; s += MG_THREADS) sK[1 + na + s] = B[j0 + s];
     if (threadIdx.x == 0) {
         W h = SENTINEL;
         if (i0 > 0) {  // A[i0 - 1]: in bucket r0 unless that bucket starts exactly at i0
@@ -130,8 +173,8 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
             h = (W)(((W)ix.bucket_prefix[rp] << P.suffix_bits) | (W)ix.suf[i0 - 1]);
         }
         sK[0] = h;
-        sK[1 + na + nb] = j1 < nB ? B[j1] : SENTINEL;
-        s_bprev = j0 > 0 ? B[j0 - 1] : SENTINEL;
+        sK[1 + na + nb] = j1 < nB ? B.at(j1, P) : SENTINEL;
+        s_bprev = (!BCSR && j0 > 0) ? B.at(j0 - 1, P) : SENTINEL;   // an index holds no repeats
     }
     __syncthreads();
 
@@ -234,7 +277,8 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
 
 // Dense per-prefix counters -> directory.  One warp handles 32 directory words (1024 prefixes):
 // coalesced counter rows, ballots give the bit words, warp sums the element counts.
-// dir[w] = {bits, rank}; word_off[w] = number of elements in prefixes below 32 * w; totals[0] = nb, totals[1] = n.
+// dir[w] = {bits, rank}; word_off[w] = number of elements in prefixes below 32 * w; totals[0] = nb, totals[1] = n
+// (the caller passes its totals array + 1: slot 0 of that array is the merge kernel's own element count).
 static __global__ void __launch_bounds__(256) dir_bits_kernel(const uint32_t* __restrict__ prefix_cnt, uint64_t n_words, uint2* __restrict__ dir,
                                                        uint32_t* __restrict__ word_off, volatile uint64_t* status_rank,
                                                        volatile uint64_t* status_off, uint32_t* tile_counter,
@@ -269,12 +313,15 @@ static __global__ void __launch_bounds__(256) dir_bits_kernel(const uint32_t* __
     }
 }
 
-// bucket_prefix / bucket_off / bucket_range of every occupied prefix (thread = directory word)
+// bucket_prefix / bucket_off / bucket_range of every occupied prefix (thread = directory word).  The bucket and
+// element totals are read from the device (totals[1] = buckets, totals[2] = elements, written by dir_bits_kernel), so
+// the host never waits for them in the middle of a mutation; totals[3] receives the prefix of the last bucket.
 static __global__ void dir_fill_kernel(const uint32_t* __restrict__ prefix_cnt, const uint2* __restrict__ dir, const uint32_t* __restrict__ word_off,
                                 uint64_t n_words, uint32_t* __restrict__ bucket_prefix, uint32_t* __restrict__ bucket_off,
-                                uint2* __restrict__ bucket_range, uint32_t nb, uint32_t n) {
+                                uint2* __restrict__ bucket_range, unsigned long long* __restrict__ totals) {
     const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w == 0) bucket_off[nb] = n;
+    const uint32_t nb = (uint32_t)totals[1];
+    if (w == 0) bucket_off[nb] = (uint32_t)totals[2];
     if (w >= n_words) return;
     const uint2 e = dir[w];
     uint32_t bits = e.x, r = e.y, o = word_off[w];
@@ -285,6 +332,7 @@ static __global__ void dir_fill_kernel(const uint32_t* __restrict__ prefix_cnt, 
         bucket_prefix[r] = p;
         bucket_off[r] = o;
         bucket_range[r] = make_uint2(o, o + c);
+        if (r + 1 == nb) totals[3] = p;
         o += c;
         r++;
     }

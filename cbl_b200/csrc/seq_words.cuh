@@ -24,9 +24,21 @@ namespace cbl {
 // A region that would overflow is not written; cnt[d] > cap afterwards tells the host to retry with a larger cap.
 // MODE 3 (owner side): membership of in_words[0, n_in), one answer byte per word to out_flags, which may itself
 // be peer memory (the answer region inside the source rank's buffer).
+constexpr int PROBE_MAX_SEG = 16;
 template <class W> struct ShardArgs {
-    const W* in_words = nullptr;          // MODE 3
-    unsigned long long n_in = 0;          // MODE 3
+    // MODE 3: the words come as up to PROBE_MAX_SEG segments (the per-source regions of a sharded receive buffer), all
+    // probed by ONE launch: segment s holds seg_n[s] words, its answers go to seg_out[s] (one byte per word; may be
+    // peer memory); seg_chunk0[s] = number of 2048-word chunks in the segments before s
+    const W* seg_words[PROBE_MAX_SEG];
+    uint8_t* seg_out[PROBE_MAX_SEG];
+    unsigned long long seg_n[PROBE_MAX_SEG];
+    unsigned long long seg_chunk0[PROBE_MAX_SEG + 1];
+    int n_seg = 0;
+    // MODE 0: digit histograms of the words for the LSD passes of the batch sort, folded into the kernel that makes
+    // the words (saves the separate read of the batch by radix_hist_kernel): hist[p][256] (u64, zeroed by the caller)
+    // counts digit hist_first + p, p < hist_np <= SW_HIST_MAX; null = no histogram
+    unsigned long long* hist = nullptr;
+    int hist_first = 0, hist_np = 0;
     DestDigit<W> dest;                    // MODE 2: owner rank of a word
     W* peer[ROUTE_MAX_SPLIT + 1];         // MODE 2
     unsigned long long* cnt = nullptr;    // MODE 2: [16] words reserved per owner (zeroed by the caller)
@@ -34,6 +46,7 @@ template <class W> struct ShardArgs {
     unsigned long long cap = 0;           // MODE 2: words per region
 };
 
+constexpr int SW_HIST_MAX = 4;      // digit histograms the words kernel can carry (the hybrid sort uses <= 4 LSD passes)
 constexpr int CHUNK_KMERS = 2048;  // src/cbl.rs:67 CHUNK_SIZE
 constexpr int SW_THREADS = 64;
 constexpr int PENDING_CAP = 64;   // per-warp queue of undecided lookups (power of two, >= 63)
@@ -137,6 +150,9 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN
     }
     __shared__ uint32_t s_fwd[2][32];
     __shared__ uint32_t s_piece;
+    __shared__ uint32_t s_hist[MODE == 0 ? SW_HIST_MAX * 256 : 1];
+    const bool do_hist = MODE == 0 && sa.hist != nullptr;
+    uint32_t hc_d0 = 0, hc_n0 = 0, hc_d1 = 0, hc_n1 = 0;   // per-lane run counters of the two top digits (MODE 0 histogram)
     // MODE 1: answers of the chunk (written out coalesced at the end) and, per warp, the queue of
     // lookups their first window did not decide.  Those are not finished on the spot (that would
     // stall the other lanes of the warp, 4 of 5 of which are already done) but collected and worked
@@ -193,18 +209,26 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN
         }
         q_push(und, s, L, R, g, a.w, slot_it);
     };
-    const uint64_t n_chunks = MODE == 3 ? div_up(sa.n_in, CHUNK_KMERS) : b.n_chunks;
+    const uint64_t n_chunks = MODE == 3 ? sa.seg_chunk0[sa.n_seg] : b.n_chunks;
     for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         int m;
         W* ow = nullptr;
         uint8_t* of = nullptr;
         uint32_t* opos = nullptr;
         uint64_t Wd = 0, H = 0;
+        const W* in_words = nullptr;   // MODE 3: first word of this chunk
         if (MODE == 3) {
-            m = (int)min((unsigned long long)CHUNK_KMERS, sa.n_in - chunk * CHUNK_KMERS);
-            of = out_flags + chunk * CHUNK_KMERS;
+            int sg = 0;
+#pragma unroll
+            for (int t = 1; t < PROBE_MAX_SEG; t++) sg += (t < sa.n_seg && sa.seg_chunk0[t] <= chunk) ? 1 : 0;
+            const uint64_t w0 = (chunk - sa.seg_chunk0[sg]) * CHUNK_KMERS;
+            m = (int)min((unsigned long long)CHUNK_KMERS, sa.seg_n[sg] - w0);
+            of = sa.seg_out[sg] + w0;
+            in_words = sa.seg_words[sg] + w0;
         } else {
             if (threadIdx.x == 0) s_piece = (uint32_t)(upper_bound_dev<uint64_t>(b.piece_chunk0, (uint64_t)b.n_pieces + 1, chunk) - 1);
+            if (do_hist)
+                for (int i = threadIdx.x; i < sa.hist_np * 256; i += SW_THREADS) s_hist[i] = 0;
             __syncthreads();
             const uint32_t piece = s_piece;
             const uint64_t ci = chunk - b.piece_chunk0[piece];
@@ -268,7 +292,7 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN
                 W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
                 slot[u] = (uint32_t)kidx;
                 if (MODE == 3) {
-                    word[u] = active[u] ? sa.in_words[chunk * CHUNK_KMERS + kidx] : (W)0;
+                    word[u] = active[u] ? in_words[kidx] : (W)0;
                     continue;
                 }
                 if (P.canonical) {
@@ -282,8 +306,27 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN
             }
             if (MODE == 0) {
 #pragma unroll
-                for (int u = 0; u < U; u++)
+                for (int u = 0; u < U; u++) {
                     if (active[u]) ow[slot[u]] = word[u];
+                    if (do_hist && active[u]) {
+                        const W v = (W)(word[u] >> (8 * sa.hist_first));
+                        const int np = sa.hist_np;
+                        for (int p = 0; p < np - 2; p++) atomicAdd(&s_hist[p * 256 + ((uint32_t)(v >> (8 * p)) & 255u)], 1u);
+                        // the two most significant digits are heavily skewed for necklace words (they start with a run of
+                        // zeros): every lane counts runs of equal digits in registers and touches shared memory only when the
+                        // digit changes (match.any aggregation cost as much ALU time as the separate histogram pass it replaced)
+                        if (np >= 2) {
+                            const uint32_t d = (uint32_t)(v >> (8 * (np - 2))) & 255u;
+                            if (d != hc_d0) { if (hc_n0) atomicAdd(&s_hist[(np - 2) * 256 + hc_d0], hc_n0); hc_d0 = d; hc_n0 = 0; }
+                            hc_n0++;
+                        }
+                        if (np >= 1) {
+                            const uint32_t d = (uint32_t)(v >> (8 * (np - 1))) & 255u;
+                            if (d != hc_d1) { if (hc_n1) atomicAdd(&s_hist[(np - 1) * 256 + hc_d1], hc_n1); hc_d1 = d; hc_n1 = 0; }
+                            hc_n1++;
+                        }
+                    }
+                }
             } else if (MODE == 2) {
 #pragma unroll
                 for (int u = 0; u < U; u++)
@@ -386,7 +429,15 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN
                 if (bd != 0xFFFFFFFFu) s_peer[d][(size_t)bd + ((uint32_t)q - s_off[d])] = s_stage[s_inv[q]];
             }
         }
-        __syncthreads();  // s_piece / s_fwd / s_flags reuse in the next grid-stride iteration
+        if (do_hist) {   // the chunk's counters: lane run counters -> shared, then one global RED per digit value that occurred
+            if (hc_n0) atomicAdd(&s_hist[(sa.hist_np - 2) * 256 + hc_d0], hc_n0);
+            if (hc_n1) atomicAdd(&s_hist[(sa.hist_np - 1) * 256 + hc_d1], hc_n1);
+            hc_n0 = hc_n1 = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < sa.hist_np * 256; i += SW_THREADS)
+                if (s_hist[i]) atomicAdd(&sa.hist[i], (unsigned long long)s_hist[i]);
+        }
+        __syncthreads();  // s_piece / s_fwd / s_flags / s_hist reuse in the next grid-stride iteration
     }
 }
 

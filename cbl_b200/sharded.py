@@ -418,10 +418,9 @@ class ShardedCBL:
 
         def probe(C, slot):
             t_p = time.perf_counter()
-            for s_ in range(self.world):   # region s of my receive buffer -> my region of rank s's answer buffer
-                n_s = int(C[s_, self.rank])
-                if n_s:
-                    cbl.words_op_dev(0, px.recv_region(s_, slot), n_s, px.answer_region(s_, slot))
+            # region s of my receive buffer -> my region of rank s's answer buffer: ONE launch over the g regions
+            cbl.words_contains_segments_dev([px.recv_region(s_, slot) for s_ in range(self.world)], C[:, self.rank],
+                                            [px.answer_region(s_, slot) for s_ in range(self.world)])
             if os.environ.get("CBL_SHARD_TRACE"):
                 print(f"[shard trace] rank {self.rank}: probe of {int(C[:, self.rank].sum())} words {(time.perf_counter() - t_p) * 1e3:.2f} ms, "
                       f"{cbl.num_buckets()} buckets, {cbl.count()} k-mers", flush=True)

@@ -21,7 +21,8 @@
  *     the value fits 64 bits;
  *   - sequences are raw nucleotide bytes (what needletail hands to the reference), batches are a
  *     concatenation + n_seqs+1 byte offsets.  A record shorter than K => CBL_EINVAL (the reference
- *     panics).  Non-ACGT bytes => CBL_EINVAL (the reference silently drops them).
+ *     panics).  Non-ACGT bytes are dropped chunk by chunk exactly like the reference does (see the note at
+ *     cbl_last_kmer_count); only the fused multi-GPU route cbl_seq_route_dev rejects them with CBL_EINVAL.
  */
 #ifndef CBL_GPU_H
 #define CBL_GPU_H
@@ -116,6 +117,9 @@ int32_t cbl_words_op_dev(cbl_t* h, int32_t op, const void* d_words, size_t n, ui
 /* insert (1) / remove (2) the words of n_seg device segments as ONE batch (the per-source regions of a sharded receive
  * buffer): the shard is rewritten once, not once per segment */
 int32_t cbl_words_op_segments_dev(cbl_t* h, int32_t op, const void* const* seg, const uint64_t* seg_n, uint32_t n_seg);
+/* membership of the words of n_seg device segments in ONE kernel launch: answers of segment i (one byte per word) go to
+ * seg_out[i], which may be peer memory (the owner-side probe of the sharded contains_seq, src/cbl.rs:311-324) */
+int32_t cbl_words_contains_segments_dev(cbl_t* h, const void* const* seg, const uint64_t* seg_n, uint8_t* const* seg_out, uint32_t n_seg);
 int32_t cbl_export_words_dev(cbl_t* h, uint64_t start, uint64_t count, void* d_out);
 /* router: stable partition of n words by owner rank, dest = number of splitters <= prefix (contiguous
  * prefix ranges).  d_send: the words grouped by destination; d_pos (may be NULL): for every input word
