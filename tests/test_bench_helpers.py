@@ -13,7 +13,10 @@ def test_build_phase_roofline_uses_survey_bytes():
     prof = {"radix_pass_kernel<W,false,ByteDigit<W>>": {"n": 3, "ms": 9.0}, "seg_sort_kernel<W,true>": {"n": 1, "ms": 6.0},
             "merge_apply_kernel<W,Suf,OP>": {"n": 1, "ms": 3.0}, "dir_fill_kernel": {"n": 1, "ms": 0.05}}
     r = bench.build_phase_roofline(prof, n, stored, peak)
-    assert set(r) == {"radix_pass_kernel", "seg_sort_kernel", "merge_apply_kernel"}
+    assert set(r) == {"radix_pass_kernel", "seg_sort_kernel", "merge_apply_kernel", "_aggregate"}
+    agg = r["_aggregate"]
+    assert agg["algorithmic_bytes"] == 3 * n * 16 + n * 16 + (n * 8 + stored * 4 + 3 * (1 << 24) * 4)
+    assert abs(agg["kernel_ms"] - 18.05) < 1e-9
     assert r["radix_pass_kernel"]["algorithmic_bytes_per_launch"] == n * 16          # read + scatter of 8-byte words
     assert abs(r["radix_pass_kernel"]["achieved_GBps"] - 3 * n * 16 / 9.0e-3 / 1e9) < 1e-6
     assert r["merge_apply_kernel"]["algorithmic_bytes_per_launch"] == n * 8 + stored * 4 + 3 * (1 << 24) * 4
