@@ -23,6 +23,22 @@ struct PieceList {
     uint64_t n_kmers = 0, n_chunks = 0;
 };
 
+// pointers of one rank's fused sharded query (producer + consumer over peer memory); g = n_split + 1 ranks
+struct FusedQuery {
+    const uint32_t* splitters;
+    uint32_t n_split;
+    void* const* peer_region;                    // [g] this rank's region inside owner d's receive buffer
+    unsigned* const* peer_ready;                 // [g] this rank's row of block counters at owner d
+    unsigned long long* const* peer_final;       // [g] this rank's final-count slot at owner d
+    uint64_t cap;                                // words per region (multiple of 2048)
+    uint32_t* d_pos;                             // [k-mers] answer slot of every local k-mer (d * cap + index inside region d)
+    const void* const* recv_region;              // [g] region of this rank's receive buffer written by source s
+    uint8_t* const* answer_region;               // [g] this rank's region inside source s's answer buffer
+    const unsigned* const* ready;                // [g] local block counters of source s
+    const unsigned long long* const* final_;     // [g] local final-count slot of source s
+    unsigned* ticket;                            // local, zero on entry
+};
+
 class IIndex {
 public:
     virtual ~IIndex() {}
@@ -52,6 +68,8 @@ public:
     virtual void route_words_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* d_send,
                                  uint32_t* d_pos, uint64_t* counts) = 0;
     virtual void gather_u8_dev(const uint8_t* d_src, const uint32_t* d_pos, uint64_t n, uint8_t* d_out) = 0;
+    virtual void seq_contains_fused_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, const FusedQuery& q,
+                                        uint64_t* counts) = 0;
     // fused route + exchange over peer memory (see include/cbl_gpu.h)
     virtual void route_counts_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, uint64_t* counts) = 0;
     virtual void route_scatter_dev(const void* d_words, uint64_t n, const uint32_t* splitters, uint32_t n_split, void* const* peer_recv,

@@ -95,7 +95,7 @@ class Index final : public IIndex {
         ~HostStage() { if (p) cudaFreeHost(p); }
     } stage_;
     cudaEvent_t stage_ev_ = nullptr;           // the last copy out of stage_ has completed
-    unsigned long long* h_status_ = nullptr;   // pinned: [0] merged elements, [1] buckets, [2] elements by the directory,
+    unsigned long long* h_status_ = nullptr;   // pinned (32 words): [0] merged elements, [1] buckets, [2] elements by the directory,
                                                // [3] last prefix, [4] segment-sort fail flag, [5] non-ACGT byte offset
 
 public:
@@ -135,7 +135,7 @@ public:
         sub_.alloc(8, st_);
         sub_.zero();
         { const char* m = getenv("CBL_SORT"); sort_hybrid_ = !(m && std::string(m) == "lsd"); }
-        CUDA_CHECK(cudaMallocHost((void**)&h_status_, 8 * sizeof(unsigned long long)));
+        CUDA_CHECK(cudaMallocHost((void**)&h_status_, 32 * sizeof(unsigned long long)));
         batch_kmers_ = env_u64("CBL_BATCH_KMERS", sizeof(W) == 8 ? (1ull << 29) : (1ull << 28));   // sort buffers: 2 x 4.3 GB of the 180 GB
         if (batch_kmers_ > RS_MAX_KEYS) batch_kmers_ = RS_MAX_KEYS;
         if (batch_kmers_ < CHUNK_KMERS) batch_kmers_ = CHUNK_KMERS;
@@ -1102,6 +1102,74 @@ public:
         CUDA_CHECK(cudaStreamSynchronize(st_));   // the stores to the peers are complete
         if (h[16] != ULLONG_MAX) throw_bad_byte(h[16]);
         for (uint32_t i = 0; i <= n_split; i++) counts[i] = h[i];
+    }
+    // The fused sharded query of one rank (see ShardArgs in seq_words.cuh): the producer (encode + necklace + route, MODE 2
+    // with block signalling) runs on a side stream, the consumer (MODE 4: probes blocks of words as the peers complete
+    // them, answers stored straight into the asking rank's buffer) on the handle's stream, both with capped, persistent
+    // grids so that they are co-resident on every SM: the integer work of the producer hides under the memory stalls of
+    // the consumer the way the two halves of the single-GPU fused kernel do, and no host round trip separates routing
+    // from probing.  Returns when both kernels are done; counts[d] = words sent to owner d (> cap: overflow, retry).
+    void seq_contains_fused_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, const FusedQuery& q,
+                                uint64_t* counts) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        check_records(offsets, n_seqs);
+        const uint32_t g = q.n_split + 1;
+        if (g > ROUTE_MAX_SPLIT + 1 || g > PROBE_MAX_SEG) throw Error(CBL_EINVAL, "too many ranks");
+        if ((uint64_t)g * q.cap >= (1ull << 32)) throw Error(CBL_EINVAL, "fused query: (ranks x region capacity) must stay below 2^32 words");
+        if (q.cap % CHUNK_KMERS) throw Error(CBL_EINVAL, "fused query: region capacity must be a multiple of 2048 words");
+        for (uint32_t i = 0; i < g; i++) counts[i] = 0;
+        cudaStream_t ps = side_[0];
+        ensure_sub();
+        int sms = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device));
+        // ---- producer
+        PieceList pl;
+        build_pieces(offsets, 0, n_seqs, pl);
+        DevPieces dp;
+        DevBuf<unsigned long long> cnt(17, ps);   // [16] per-owner counters, [16] = error offset
+        CUDA_CHECK(cudaMemsetAsync(cnt.get(), 0, 16 * 8, ps));
+        CUDA_CHECK(cudaMemsetAsync(cnt.get() + 16, 0xFF, 8, ps));
+        if (!pl.kmers.empty()) {
+            upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, ps);
+            ShardArgs<W> sa{};
+            sa.dest = make_dest_digit(q.splitters, q.n_split);
+            for (uint32_t i = 0; i <= ROUTE_MAX_SPLIT; i++) {
+                sa.peer[i] = i < g ? (W*)q.peer_region[i] : nullptr;
+                sa.peer_ready[i] = i < g ? q.peer_ready[i] : nullptr;
+            }
+            sa.cnt = cnt.get();
+            sa.pos = q.d_pos;
+            sa.cap = q.cap;
+            const unsigned grid = (unsigned)std::min<uint64_t>(dp.batch.n_chunks, (uint64_t)sms * env_u64("CBL_FUSED_PROD", 6));
+            CBL_LAUNCH((seq_words_kernel<W, Suf, 2, false, 32, 1>), grid, SW_THREADS, 0, ps, dp.batch, P_, (W*)nullptr, (uint8_t*)nullptr, view(),
+                       cnt.get() + 16, sa);
+        }
+        {
+            PeerFinals pf;
+            for (uint32_t i = 0; i <= ROUTE_MAX_SPLIT; i++) pf.p[i] = i < g ? q.peer_final[i] : nullptr;
+            CBL_LAUNCH(publish_finals_kernel, 1, 32, 0, ps, cnt.get(), (unsigned long long)q.cap, pf, (int)g);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(h_status_, cnt.get(), 17 * 8, cudaMemcpyDeviceToHost, ps));
+        // ---- consumer
+        {
+            ShardArgs<W> sa{};
+            for (uint32_t i = 0; i < g; i++) {
+                sa.seg_words[i] = (const W*)q.recv_region[i];
+                sa.seg_out[i] = q.answer_region[i];
+                sa.ready[i] = q.ready[i];
+                sa.final_[i] = q.final_[i];
+            }
+            sa.n_seg = (int)g;
+            sa.ticket = q.ticket;
+            sa.max_blocks = (uint32_t)(q.cap / CHUNK_KMERS);
+            const unsigned grid = (unsigned)((uint64_t)sms * env_u64("CBL_FUSED_CONS", 10));
+            CBL_LAUNCH((seq_words_kernel<W, Suf, 4, false, CBL_PROBE_WB, 1>), grid, SW_THREADS, 0, st_, SeqBatch{}, P_, (W*)nullptr, (uint8_t*)nullptr,
+                       view(), (unsigned long long*)nullptr, sa);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ps));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        if (h_status_[16] != ULLONG_MAX) throw_bad_byte(h_status_[16]);
+        for (uint32_t i = 0; i < g; i++) counts[i] = h_status_[i];
     }
     void gather_u8_dev(const uint8_t* d_src, const uint32_t* d_pos, uint64_t n, uint8_t* d_out) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));

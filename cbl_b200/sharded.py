@@ -184,9 +184,10 @@ class PeerExchange:
         backend = dist.get_backend(group)
         self.ctrl = torch.device("cpu") if backend == "gloo" else device
         self.cap = 0        # words per region
-        self.own_recv = self.own_back = 0
+        self.own_recv = self.own_back = self.own_ctrl = 0
         self.peer_recv: List[int] = []
         self.peer_back: List[int] = []
+        self.peer_ctrl: List[int] = []   # control blocks of the fused query: block counters, final counts, ticket
 
     def barrier(self):
         if self.ctrl.type == "cpu":
@@ -208,13 +209,15 @@ class PeerExchange:
         for r, p in enumerate(self.peer_back):
             if r != self.rank and p:
                 self.cbl.peer_close(p)
-        self.peer_recv, self.peer_back = [], []
+        for r, p in enumerate(self.peer_ctrl):
+            if r != self.rank and p:
+                self.cbl.peer_close(p)
+        self.peer_recv, self.peer_back, self.peer_ctrl = [], [], []
         self.barrier()  # nobody maps our blocks any more
-        if self.own_recv:
-            self.cbl.peer_free(self.own_recv)
-        if self.own_back:
-            self.cbl.peer_free(self.own_back)
-        self.own_recv = self.own_back = 0
+        for p in (self.own_recv, self.own_back, self.own_ctrl):
+            if p:
+                self.cbl.peer_free(p)
+        self.own_recv = self.own_back = self.own_ctrl = 0
 
     def ensure(self, cap_words: int):
         """Collective: every rank calls it with the same argument."""
@@ -226,11 +229,34 @@ class PeerExchange:
             raise ValueError("batch too large for one exchange: split the reads into smaller batches")
         self.own_recv, h_recv = self.cbl.peer_alloc(self.SLOTS * self.world * self.cap * self.word_bytes)
         self.own_back, h_back = self.cbl.peer_alloc(self.SLOTS * self.world * self.cap)
+        self.own_ctrl, h_ctrl = self.cbl.peer_alloc(self.ctrl_bytes())
         handles = [None] * self.world
-        dist.all_gather_object(handles, (h_recv, h_back), group=self.group)
+        dist.all_gather_object(handles, (h_recv, h_back, h_ctrl), group=self.group)
         self.peer_recv = [self.own_recv if r == self.rank else self.cbl.peer_open(handles[r][0]) for r in range(self.world)]
         self.peer_back = [self.own_back if r == self.rank else self.cbl.peer_open(handles[r][1]) for r in range(self.world)]
+        self.peer_ctrl = [self.own_ctrl if r == self.rank else self.cbl.peer_open(handles[r][2]) for r in range(self.world)]
+        self.cbl.peer_zero(self.own_ctrl, self.ctrl_bytes())
         self.barrier()
+
+    # control block of the fused query (one per rank, peer-mapped): [world rows of cap/2048 u32 block counters]
+    # [world u64 final counts][u32 ticket]; row / slot s belongs to source rank s
+    def blocks(self) -> int:
+        return self.cap // 2048
+
+    def ctrl_bytes(self) -> int:
+        return self.world * self.blocks() * 4 + self.world * 8 + 64
+
+    def ready_row(self, base: int, src: int) -> int:
+        return base + src * self.blocks() * 4
+
+    def final_slot(self, base: int, src: int) -> int:
+        return base + self.world * self.blocks() * 4 + src * 8
+
+    def ticket(self) -> int:
+        return self.own_ctrl + self.world * self.blocks() * 4 + self.world * 8
+
+    def zero_ctrl(self):
+        self.cbl.peer_zero(self.own_ctrl, self.ctrl_bytes())
 
     def my_regions(self, slot: int = 0) -> List[int]:
         """my region inside every owner's receive buffer (buffer set ``slot``)"""
@@ -366,7 +392,10 @@ class ShardedCBL:
         """Per-k-mer answers (uint8 device tensor) for this rank's reads, in the reference's order
         (src/cbl.rs:311-324)."""
         if self.peer is not None:
-            return self._peer_contains(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+            if int(os.environ.get("CBL_FUSED", self.FUSED)):
+                return self._peer_contains_fused(d_buf, offsets)
+            return self._peer_contains(d_buf, offsets)
         words = self.engine.seq_words(d_buf, np.ascontiguousarray(offsets, dtype=np.uint64))
         return self.contains_words(words)
 
@@ -374,6 +403,44 @@ class ShardedCBL:
     # (bench.py, 1 Gbp per rank): 4 sub-batches 53.6 ms per step, 1 sub-batch 50.7 ms — the route and probe kernels contend
     # for the same SM resources when co-resident (each slows down by what the other takes), so the default is 1.
     PIPE = 1
+
+    FUSED = 1   # CBL_FUSED=0: route kernel, count exchange, probe kernel one after the other (the round-1 path)
+
+    def _peer_contains_fused(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
+        """contains_seq of this rank's reads as ONE producer + ONE consumer kernel per rank (cbl_seq_contains_fused_dev): words
+        travel to their owners and answers back over NVLink peer memory while both kernels run; the process group only
+        carries two small count exchanges per call (region sizing / "everything has landed")."""
+        px, cbl = self.peer, self.engine.cbl
+        n = cbl.count_kmers(offsets)
+        # doubles as the barrier "every rank is done with the buffers of the previous call"
+        n_max = int(px.all_counts(np.array([n], dtype=np.uint64)).max())
+        cap = int(n_max / self.world * float(os.environ.get("CBL_ROUTE_SLACK", self.SLACK))) + 4096
+        pos = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        g, me = self.world, self.rank
+        while True:
+            px.ensure(cap)
+            px.zero_ctrl()
+            px.barrier()                                             # every rank's counters are zero before anybody produces
+            counts = cbl.seq_contains_fused_dev(
+                d_buf, offsets, self.splitters_u32,
+                peer_region=px.my_regions(),
+                peer_ready=[px.ready_row(px.peer_ctrl[d], me) for d in range(g)],
+                peer_final=[px.final_slot(px.peer_ctrl[d], me) for d in range(g)],
+                cap=px.cap, d_pos=pos.data_ptr(),
+                recv_region=[px.recv_region(s_) for s_ in range(g)],
+                answer_region=[px.answer_region(s_) for s_ in range(g)],
+                ready=[px.ready_row(px.own_ctrl, s_) for s_ in range(g)],
+                final_counts=[px.final_slot(px.own_ctrl, s_) for s_ in range(g)],
+                ticket=px.ticket())
+            C = px.all_counts(counts)                                # barrier: every consumer is done => my answers have landed
+            if int(C.max()) <= px.cap:
+                break
+            cap = int(int(C.max()) * 1.1) + 4096                     # a region overflowed somewhere: everybody retries
+        if n:
+            cbl.gather_u8_dev(px.answers(), pos.data_ptr(), n, out.data_ptr())
+        return out
 
     def _peer_contains(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
         """Pipelined query over peer memory.  The reads are cut into PIPE sub-batches of whole records.  Sub-batch b:

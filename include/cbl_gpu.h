@@ -154,6 +154,22 @@ int32_t cbl_route_scatter_dev(cbl_t* h, const void* d_words, size_t n, const uin
  * d_out = that peer pointer).  (n_splitters+1) * cap < 2^32.  Returns when the stores are complete. */
 int32_t cbl_seq_route_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, const uint32_t* splitters,
                           uint32_t n_splitters, void* const* peer_region, uint64_t cap, uint32_t* d_pos, uint64_t* counts);
+/* The fused sharded contains_seq of one rank: ONE producer kernel (2-bit encode + necklace + route, every word stored
+ * straight into its owner's receive buffer over NVLink) and ONE consumer kernel (membership probe of the words the peers
+ * stored here, every answer stored straight back into the asking rank's answer buffer) run side by side on every SM; the
+ * producer tells the owners which 2048-word blocks of its regions are complete through counters in peer memory, so no
+ * host round trip or collective separates routing from probing (src/cbl.rs:311-324 for a prefix-sharded set).
+ * Arrays of g = n_splitters + 1 pointers, indexed by rank: peer_region / peer_ready / peer_final = THIS rank's region
+ * (cap words, cap a multiple of 2048), row of cap / 2048 u32 block counters and u64 final-count slot at owner d;
+ * recv_region / ready / final_counts = the same objects of source s in THIS rank's own buffers; answer_region = this
+ * rank's region (cap bytes) in source s's answer buffer; ticket = a zeroed u32.  All counters must be zero on every
+ * rank before any rank calls (zero with cbl_peer_zero, then a barrier).  d_pos and counts as for cbl_seq_route_dev.
+ * Returns when both kernels of THIS rank are done; a barrier over all ranks then guarantees every answer has landed. */
+int32_t cbl_seq_contains_fused_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, const uint32_t* splitters,
+                                   uint32_t n_splitters, void* const* peer_region, void* const* peer_ready, void* const* peer_final, uint64_t cap,
+                                   uint32_t* d_pos, const void* const* recv_region, uint8_t* const* answer_region, const void* const* ready,
+                                   const void* const* final_counts, void* ticket, uint64_t* counts);
+int32_t cbl_peer_zero(cbl_t* h, void* d_ptr, size_t bytes);           /* zero a block of (own) device memory, synchronous */
 int32_t cbl_word_bytes(const cbl_t* h, int32_t* out);      /* 8 or 16: size of one device word */
 int32_t cbl_suffix_bits(const cbl_t* h, int32_t* out);
 
