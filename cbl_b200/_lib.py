@@ -20,6 +20,9 @@ vpp = C.POINTER(C.c_void_p)
 # every symbol include/cbl_gpu.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "cbl_create": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, vpp]),
+    "cbl_create_sharded": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, i32p, vpp]),
+    "cbl_create_sharded_ex": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, i32p, u32p, vpp]),
+    "cbl_sharded_splitters": (C.c_int32, [vp, u32p, C.c_size_t, szp]),
     "cbl_destroy": (C.c_int32, [vp]),
     "cbl_clone": (C.c_int32, [vp, vpp]),
     "cbl_last_error": (C.c_char_p, [vp]),

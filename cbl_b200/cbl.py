@@ -75,6 +75,30 @@ class CBL:
     def new_canonical(cls, k: int, t_bits: int, prefix_bits: int = 24, device: int = 0) -> "CBL":
         return cls(k, t_bits, prefix_bits, True, device)
 
+    @classmethod
+    def sharded(cls, k: int, t_bits: int, prefix_bits: int = 24, canonical: bool = False, devices: Sequence[int] = (0,),
+                splitters: Optional[Sequence[int]] = None) -> "CBL":
+        """One set prefix-sharded over ``devices`` (GPUs of THIS process) behind the same handle type: every host-buffer
+        method works unchanged (``cbl_create_sharded``); the ``*_dev`` methods raise."""
+        L = _lib.lib()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        if splitters is None:
+            rc = L.cbl_create_sharded(k, t_bits, prefix_bits, int(canonical), len(devices), devs, C.byref(h))
+        else:
+            sp = (C.c_uint32 * max(len(splitters), 1))(*[int(x) for x in splitters])
+            rc = L.cbl_create_sharded_ex(k, t_bits, prefix_bits, int(canonical), len(devices), devs, sp, C.byref(h))
+        if rc:
+            raise CBLError(rc, L.cbl_last_global_error().decode())
+        return cls(k, t_bits, prefix_bits, canonical, int(devices[0]), _handle=h)
+
+    def shard_splitters(self) -> np.ndarray:
+        n = C.c_size_t()
+        self._chk(self._L.cbl_sharded_splitters(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.uint32)
+        self._chk(self._L.cbl_sharded_splitters(self._h, out.ctypes.data_as(u32p), len(out), C.byref(n)))
+        return out[: n.value]
+
     # -- plumbing --------------------------------------------------------------------------------
     def _wrap(self, h) -> "CBL":
         return CBL(self.k, self.t_bits, self.prefix_bits, device=self.device, _handle=h)

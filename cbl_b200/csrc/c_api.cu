@@ -133,10 +133,9 @@ void read_trie(Reader& r, int depth, int BYTES, unsigned __int128 acc, unsigned 
 
 cbl_handle* deserialize_index(const cbl_handle* proto, const uint8_t* data, size_t len) {
     Reader r{data, len};
-    Config cfg = proto->ix->config();
-    cfg.canonical = r.u8() ? 1 : 0;
+    const int canonical = r.u8() ? 1 : 0;
     std::unique_ptr<cbl_handle> h(new cbl_handle());
-    h->ix.reset(make_index(cfg));
+    h->ix.reset(proto->ix->new_empty(canonical));   // same K / T / PREFIX_BITS / device(s) (and splitters) as the prototype
     const KParams& P = h->ix->params();
     const int BYTES = (P.suffix_bits + 7) / 8;
     uint64_t nb = r.varint();
@@ -185,6 +184,31 @@ int32_t cbl_create(uint32_t k, uint32_t word_bits, uint32_t prefix_bits, int32_t
         std::unique_ptr<cbl_handle> h(new cbl_handle());
         h->ix.reset(make_index(cfg));
         *out = h.release();
+    });
+}
+int32_t cbl_create_sharded_ex(uint32_t k, uint32_t word_bits, uint32_t prefix_bits, int32_t canonical, int32_t n_gpus, const int32_t* devices,
+                              const uint32_t* splitters, cbl_t** out) {
+    return guard(nullptr, [&] {
+        need(out, "out"); need(devices, "devices");
+        Config cfg{(int)k, (int)word_bits, (int)prefix_bits, canonical ? 1 : 0, devices[0]};
+        std::unique_ptr<cbl_handle> h(new cbl_handle());
+        h->ix.reset(make_sharded_index(cfg, devices, n_gpus, splitters));
+        *out = h.release();
+    });
+}
+int32_t cbl_create_sharded(uint32_t k, uint32_t word_bits, uint32_t prefix_bits, int32_t canonical, int32_t n_gpus, const int32_t* devices, cbl_t** out) {
+    return cbl_create_sharded_ex(k, word_bits, prefix_bits, canonical, n_gpus, devices, nullptr, out);
+}
+int32_t cbl_sharded_splitters(cbl_t* h, uint32_t* out, size_t cap, size_t* n_out) {
+    return guard(h, [&] {
+        need(h, "handle"); need(n_out, "n_out");
+        std::vector<uint32_t> sp;
+        if (!sharded_splitters(h->ix.get(), sp)) throw Error(CBL_EINVAL, "not a sharded handle");
+        *n_out = sp.size();
+        if (out) {
+            if (cap < sp.size()) throw Error(CBL_EINVAL, "output buffer too small");
+            for (size_t i = 0; i < sp.size(); i++) out[i] = sp[i];
+        }
     });
 }
 int32_t cbl_destroy(cbl_t* h) {

@@ -49,6 +49,7 @@ public:
     virtual uint32_t n_buckets() const = 0;
     virtual bool is_empty_reference_semantics() const = 0;
     virtual IIndex* clone() = 0;
+    virtual IIndex* new_empty(int canonical = -1) = 0;   // (canonical < 0: same flag) an empty set with the same parameters (and, for a sharded set, devices and splitters)
     // sequences: `d_seq` device pointer to n_bytes bytes, host offsets[n_seqs + 1]
     virtual void insert_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs) = 0;
     virtual void remove_seqs_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs) = 0;
@@ -60,6 +61,8 @@ public:
     virtual void seq_words(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, uint64_t* lo, uint64_t* hi, bool brute) = 0;
     // k-mer integers
     virtual void kmers_op(int op /*0 contains,1 insert,2 remove*/, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out) = 0;
+    // words on the host: op 0 contains, 1 insert, 2 remove; out (may be null) = membership before the call
+    virtual void words_op(int op, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out) = 0;
     // words (already transformed) — used by the sharded multi-GPU path after the all-to-all
     virtual void words_op_dev(int op, const void* d_words, uint64_t n, uint8_t* d_out) = 0;
     virtual void words_op_segments_dev(int op, const void* const* seg, const uint64_t* seg_n, uint32_t n_seg) = 0;
@@ -92,6 +95,9 @@ public:
 };
 
 IIndex* make_index(const Config& cfg);
+// one set prefix-sharded over several GPUs of this process (sharded_index.cu); splitters: n_gpus - 1 ascending prefixes or null
+IIndex* make_sharded_index(const Config& cfg, const int* devices, int n_gpus, const uint32_t* splitters);
+bool sharded_splitters(IIndex* ix, std::vector<uint32_t>& out);   // false when ix is not a sharded set
 std::string prof_report();
 uint64_t total_kmers_of(const Config& cfg, const uint64_t* offsets, size_t n_seqs);
 

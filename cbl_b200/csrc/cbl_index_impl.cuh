@@ -219,6 +219,11 @@ public:
         c->sync();
         return c.release();
     }
+    IIndex* new_empty(int canonical = -1) override {
+        Config c = cfg_;
+        if (canonical >= 0) c.canonical = canonical;
+        return new Index(c);
+    }
     void copy_state_from(const Index& o) {
         nb_ = o.nb_; n_ = o.n_; last_prefix_ = o.last_prefix_;
         sub_valid_ = false;
@@ -973,6 +978,19 @@ public:
         CBL_LAUNCH((kmers_to_words_kernel<W>), (unsigned)div_up(n, 256), 256, 0, st_, dlo.get(), hi ? dhi.get() : nullptr, (uint64_t)n, P_, w.get());
         DevBuf<uint8_t> flags(n, st_);
         words_op_dev(op, w.get(), n, out ? flags.get() : nullptr);
+        if (out) CUDA_CHECK(cudaMemcpyAsync(out, flags.get(), n, cudaMemcpyDeviceToHost, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
+    void words_op(int op, const uint64_t* lo, const uint64_t* hi, size_t n, uint8_t* out) override {
+        CUDA_CHECK(cudaSetDevice(cfg_.device));
+        if (n == 0) return;
+        std::vector<W> h(n);
+        for (size_t i = 0; i < n; i++) h[i] = sizeof(W) == 16 ? (W)(((u128)(hi ? hi[i] : 0) << 64) | lo[i]) : (W)lo[i];
+        DevBuf<W> d(n, st_);
+        DevBuf<uint8_t> flags(n, st_);
+        CUDA_CHECK(cudaMemcpyAsync(d.get(), h.data(), n * sizeof(W), cudaMemcpyHostToDevice, st_));
+        CUDA_CHECK(cudaStreamSynchronize(st_));
+        words_op_dev(op, d.get(), n, out ? flags.get() : nullptr);
         if (out) CUDA_CHECK(cudaMemcpyAsync(out, flags.get(), n, cudaMemcpyDeviceToHost, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
     }

@@ -43,12 +43,26 @@ public:
         if (rc) throw Panic(rc, cbl_last_global_error());
     }
     static CBL new_canonical(int device = 0) { return CBL(true, device); }
+    // the same set prefix-sharded over several GPUs of this process (cbl_create_sharded): every method below works unchanged
+    static CBL sharded(const std::vector<int>& devices, bool canonical = false) {
+        cbl_t* h = nullptr;
+        std::vector<int32_t> d(devices.begin(), devices.end());
+        int32_t rc = cbl_create_sharded(K, sizeof(T) * 8, PREFIX_BITS, canonical, (int32_t)d.size(), d.data(), &h);
+        if (rc) throw Panic(rc, cbl_last_global_error());
+        return CBL(h);
+    }
     ~CBL() { if (h_) cbl_destroy(h_); }
     CBL(CBL&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
     CBL& operator=(CBL&& o) noexcept { if (this != &o) { if (h_) cbl_destroy(h_); h_ = o.h_; o.h_ = nullptr; } return *this; }
     CBL(const CBL& o) { int32_t rc = cbl_clone(o.h_, &h_); if (rc) throw Panic(rc, cbl_last_error(o.h_)); }  // Clone
     CBL& operator=(const CBL& o) { if (this != &o) { CBL t(o); std::swap(h_, t.h_); } return *this; }
     cbl_t* handle() const { return h_; }
+    // Default-like: an empty set laid out like this one (same canonical flag, device(s) and splitters)
+    CBL new_like() const {
+        CBL c(*this);
+        c -= c;   // x - x = {}  (src/cbl.rs:488-510)
+        return c;
+    }
 
     bool is_canonical() const { int32_t v; chk(cbl_is_canonical(h_, &v)); return v != 0; }
     size_t count() const { uint64_t v; chk(cbl_count(h_, &v)); return (size_t)v; }
@@ -117,9 +131,13 @@ public:
     void save_to_file(const char* path) { chk(cbl_save_to_file(h_, path)); }
     static CBL load_from_file(const char* path, int device = 0) {
         CBL proto(false, device);
+        return proto.load_like(path);
+    }
+    // load into a set laid out like this one (same device, or same devices + splitters for a sharded set)
+    CBL load_like(const char* path) const {
         cbl_t* out = nullptr;
-        int32_t rc = cbl_load_from_file(proto.h_, path, &out);
-        if (rc) throw Panic(rc, cbl_last_error(proto.h_));
+        int32_t rc = cbl_load_from_file(h_, path, &out);
+        if (rc) throw Panic(rc, cbl_last_error(h_));
         return CBL(out);
     }
 

@@ -42,6 +42,17 @@ enum { CBL_OP_OR = 0, CBL_OP_AND = 1, CBL_OP_SUB = 2, CBL_OP_XOR = 3 };
 /* ---- life cycle: CBL::new / new_canonical (src/cbl.rs:71-79), Clone, Drop ------------------- */
 /* k: K; word_bits: bits of T (32/64/128, checked like src/cbl.rs:87-91); prefix_bits: PREFIX_BITS */
 int32_t cbl_create(uint32_t k, uint32_t word_bits, uint32_t prefix_bits, int32_t canonical, int32_t device, cbl_t** out);
+/* One set prefix-sharded over n_gpus GPUs of THIS process (the boundary the survey specified): the
+ * 2^PREFIX_BITS prefix space is cut into n_gpus contiguous ranges, shard i lives on devices[i]; every host-buffer
+ * entry point below works on the handle (records are split over the GPUs, words travel to their owners over NVLink
+ * peer memory, answers come back in read order; | & - ^ run shard by shard between handles created with the same
+ * devices; iteration / export / serialisation see ONE ascending set).  The *_dev entry points (device pointers of one
+ * GPU) return CBL_EINVAL on such a handle.  _ex: explicit splitters (n_gpus - 1 ascending prefixes) instead of the
+ * built-in sample-based ones; cbl_sharded_splitters reads them back (out may be NULL to query the count). */
+int32_t cbl_create_sharded(uint32_t k, uint32_t word_bits, uint32_t prefix_bits, int32_t canonical, int32_t n_gpus, const int32_t* devices, cbl_t** out);
+int32_t cbl_create_sharded_ex(uint32_t k, uint32_t word_bits, uint32_t prefix_bits, int32_t canonical, int32_t n_gpus, const int32_t* devices,
+                              const uint32_t* splitters, cbl_t** out);
+int32_t cbl_sharded_splitters(cbl_t* h, uint32_t* out, size_t cap, size_t* n_out);
 int32_t cbl_destroy(cbl_t* h);
 int32_t cbl_clone(cbl_t* h, cbl_t** out);
 const char* cbl_last_error(const cbl_t* h);

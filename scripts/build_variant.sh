@@ -4,4 +4,4 @@
 set -e
 cd "$(dirname "$0")/../cbl_b200/csrc"
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr \
-  -DCBL_FAST_BUILD $2 -shared -o libcbl_gpu_var_$1.so cbl_index.cu c_api.cu inst_u64_u32.cu -cudart static
+  -DCBL_FAST_BUILD $2 -shared -o libcbl_gpu_var_$1.so cbl_index.cu c_api.cu sharded_index.cu inst_u64_u32.cu -cudart static
