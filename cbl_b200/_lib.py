@@ -56,6 +56,7 @@ SIGNATURES = {
     "cbl_serialize_size": (C.c_int32, [vp, szp]),
     "cbl_serialize": (C.c_int32, [vp, vp, C.c_size_t, szp]),
     "cbl_deserialize": (C.c_int32, [vp, vp, C.c_size_t, vpp]),
+    "cbl_deserialize_range": (C.c_int32, [vp, vp, C.c_size_t, C.c_uint64, C.c_uint64, vpp]),
     "cbl_save_to_file": (C.c_int32, [vp, C.c_char_p]),
     "cbl_load_from_file": (C.c_int32, [vp, C.c_char_p, vpp]),
     "cbl_seq_words_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t, vp]),

@@ -449,6 +449,13 @@ class CBL:
         self._chk(self._L.cbl_deserialize(self._h, a.ctypes.data, len(a), C.byref(h)))
         return self._wrap(h)
 
+    def deserialize_range(self, data: bytes, prefix_lo: int, prefix_hi: int) -> "CBL":
+        """Like ``deserialize`` but keeps only the buckets with prefix in [prefix_lo, prefix_hi) (one rank's range)."""
+        a = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        self._chk(self._L.cbl_deserialize_range(self._h, a.ctypes.data, len(a), prefix_lo, prefix_hi, C.byref(h)))
+        return self._wrap(h)
+
     def save_to_file(self, path: str) -> None:
         self._chk(self._L.cbl_save_to_file(self._h, path.encode()))
 

@@ -131,7 +131,8 @@ void read_trie(Reader& r, int depth, int BYTES, unsigned __int128 acc, unsigned 
     for (uint64_t i = 0; i < c; i++) read_trie(r, depth + 1, BYTES, (acc << 8) | idx[i], prefix_part, suffix_bits, lo, hi);
 }
 
-cbl_handle* deserialize_index(const cbl_handle* proto, const uint8_t* data, size_t len) {
+// prefix_lo / prefix_hi: keep only the buckets with prefix in [prefix_lo, prefix_hi) (one rank's range of a sharded set)
+cbl_handle* deserialize_index(const cbl_handle* proto, const uint8_t* data, size_t len, uint64_t prefix_lo = 0, uint64_t prefix_hi = ~0ull) {
     Reader r{data, len};
     const int canonical = r.u8() ? 1 : 0;
     std::unique_ptr<cbl_handle> h(new cbl_handle());
@@ -145,6 +146,9 @@ cbl_handle* deserialize_index(const cbl_handle* proto, const uint8_t* data, size
         if (prefix >> P.prefix_bits) throw Error(CBL_EIO, "prefix out of range in serialized index");
         unsigned __int128 pp = (unsigned __int128)prefix << P.suffix_bits;
         uint64_t variant = r.varint();
+        const size_t keep_from = lo.size();
+        const bool keep = prefix >= prefix_lo && prefix < prefix_hi;
+        struct Drop { std::vector<uint64_t>&a, &b; size_t n; bool keep; ~Drop() { if (!keep) { a.resize(n); b.resize(n); } } } drop{lo, hi, keep_from, keep};
         if (variant == 0) {
             uint64_t m = r.varint();
             for (uint64_t i = 0; i < m; i++) {
@@ -366,6 +370,9 @@ int32_t cbl_serialize(cbl_t* h, uint8_t* out, size_t cap, size_t* n_out) {
 }
 int32_t cbl_deserialize(const cbl_t* proto, const uint8_t* data, size_t len, cbl_t** out) {
     return guard(mut(proto), [&] { need(proto, "proto"); need(data, "data"); need(out, "out"); *out = deserialize_index(proto, data, len); });
+}
+int32_t cbl_deserialize_range(const cbl_t* proto, const uint8_t* data, size_t len, uint64_t prefix_lo, uint64_t prefix_hi, cbl_t** out) {
+    return guard(mut(proto), [&] { need(proto, "proto"); need(data, "data"); need(out, "out"); *out = deserialize_index(proto, data, len, prefix_lo, prefix_hi); });
 }
 int32_t cbl_save_to_file(cbl_t* h, const char* path) {
     return guard(h, [&] {

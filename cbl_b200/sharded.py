@@ -110,12 +110,38 @@ def equal_mass_splitters(prefixes: torch.Tensor, world: int, tail_cost: float = 
 class GpuEngine:
     """Adapter: ``cbl_b200.CBL`` on the local GPU behind the interface the router needs."""
 
-    def __init__(self, k, t_bits, prefix_bits, canonical, device):
+    def __init__(self, k, t_bits, prefix_bits, canonical, device, cbl=None):
         from .cbl import CBL
 
-        self.cbl = CBL(k, t_bits, prefix_bits, canonical, device)
+        self.cbl = cbl if cbl is not None else CBL(k, t_bits, prefix_bits, canonical, device)
+        self.params = (k, t_bits, prefix_bits, canonical, device)
         self.device = torch.device("cuda", device)
         self.word_bytes = self.cbl.word_bytes()
+
+    def _wrap(self, cbl) -> "GpuEngine":
+        return GpuEngine(*self.params, cbl=cbl)
+
+    # shard-local set algebra, clone, export, serde (what ShardedCBL composes rank by rank)
+    def setop(self, op: int, other: "GpuEngine") -> "GpuEngine":
+        return self._wrap(self.cbl._binary(op, other.cbl))
+
+    def setop_assign(self, op: int, other: "GpuEngine") -> None:
+        self.cbl._assign(op, other.cbl)
+
+    def clone(self) -> "GpuEngine":
+        return self._wrap(self.cbl.clone())
+
+    def words_list(self) -> List[int]:
+        return self.cbl.words()
+
+    def kmers_list(self) -> List[int]:
+        return list(self.cbl.iter())
+
+    def serialize(self) -> bytes:
+        return self.cbl.serialize()
+
+    def deserialize_range(self, data: bytes, lo: int, hi: int) -> "GpuEngine":
+        return self._wrap(self.cbl.deserialize_range(data, lo, hi))
 
     def seq_words(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
         n = self.cbl.count_kmers(offsets)
@@ -565,6 +591,128 @@ class ShardedCBL:
             return ans.cpu().numpy()
         torch.from_numpy(out)[: ans.numel()].copy_(ans)
         return out[: ans.numel()]
+
+    # -- set algebra, clone, iteration, serde: shard-local, composed in rank order (src/cbl.rs:411-569, 358-360, 127-160) ----
+    def _derive(self, engine) -> "ShardedCBL":
+        """a set with the same parameters, process group and splitters around another shard-local engine (collective
+        only in so far as every rank does it; no communication)"""
+        return ShardedCBL(self.k, self.t_bits, self.prefix_bits, self.canonical, device=self.device.index or 0, engine=engine,
+                          splitters=[int(x) for x in self.splitters_u32], group=self.group)
+
+    def _check(self, other: "ShardedCBL") -> None:
+        if (other.k, other.t_bits, other.prefix_bits) != (self.k, self.t_bits, self.prefix_bits):
+            raise ValueError("set operation between indexes with different K / T / PREFIX_BITS")
+        if other.canonical != self.canonical:
+            raise ValueError("One of the index is canonical while the other isn't")   # src/cbl.rs:422-425
+        if other.world != self.world or list(other.splitters_u32) != list(self.splitters_u32):
+            raise ValueError("set operation between indexes sharded differently (ranks / splitters)")
+
+    def _binary(self, op: int, other: "ShardedCBL") -> "ShardedCBL":
+        self._check(other)
+        return self._derive(self.engine.setop(op, other.engine))   # prefix ranges coincide: the op is shard-local
+
+    def _assign(self, op: int, other: "ShardedCBL") -> "ShardedCBL":
+        self._check(other)
+        self.engine.setop_assign(op, other.engine)
+        return self
+
+    def __or__(self, o): return self._binary(0, o)
+    def __and__(self, o): return self._binary(1, o)
+    def __sub__(self, o): return self._binary(2, o)
+    def __xor__(self, o): return self._binary(3, o)
+    def __ior__(self, o): return self._assign(0, o)
+    def __iand__(self, o): return self._assign(1, o)
+    def __isub__(self, o): return self._assign(2, o)
+    def __ixor__(self, o): return self._assign(3, o)
+
+    def clone(self) -> "ShardedCBL":
+        return self._derive(self.engine.clone())
+
+    def local_words(self) -> List[int]:
+        """this rank's words, ascending: the slice [splitter[rank-1], splitter[rank]) of the global ascending set"""
+        return self.engine.words_list()
+
+    def _gather_lists(self, local):
+        if self.world == 1:
+            return [local]
+        parts = [None] * self.world
+        dist.all_gather_object(parts, local, group=self.group)
+        return parts
+
+    def words(self) -> List[int]:
+        """the whole set in ascending word order on every rank = the shards concatenated in rank order (test scale: the
+        lists travel as Python objects; at scale use local_words() / save_to_file())"""
+        return [w for part in self._gather_lists(self.local_words()) for w in part]
+
+    def iter(self):
+        """CBL::iter (src/cbl.rs:358-360): the stored k-mers in ascending word order, gathered like words()"""
+        return iter([x for part in self._gather_lists(self.engine.kmers_list()) for x in part])
+
+    __iter__ = iter
+
+    def is_empty(self) -> bool:
+        return self.count() == 0
+
+    def my_prefix_range(self):
+        lo = int(self.splitters_u32[self.rank - 1]) if self.rank > 0 else 0
+        hi = int(self.splitters_u32[self.rank]) if self.rank < self.world - 1 else 1 << self.prefix_bits
+        return lo, hi
+
+    @staticmethod
+    def _varint(v: int) -> bytes:   # bincode 1.3 varint (SURVEY section 8 row f1)
+        if v < 251:
+            return bytes([v])
+        if v <= 0xFFFF:
+            return b"\xfb" + v.to_bytes(2, "little")
+        if v <= 0xFFFFFFFF:
+            return b"\xfc" + v.to_bytes(4, "little")
+        return b"\xfd" + v.to_bytes(8, "little")
+
+    @staticmethod
+    def _read_varint(b: bytes, at: int):
+        t = b[at]
+        if t < 251:
+            return t, at + 1
+        n = {251: 2, 252: 4, 253: 8}[t]
+        return int.from_bytes(b[at + 1 : at + 1 + n], "little"), at + 1 + n
+
+    def save_to_file(self, path: str) -> None:
+        """ONE file in the reference's layout (src/cbl.rs:127-141): [canonical][bucket count][entries by ascending prefix] —
+        every rank serialises its shard, the bodies are written in rank order behind a header with the summed bucket count.
+        Collective; the path must be visible to every rank (one box)."""
+        data = self.engine.serialize()
+        nb, at = self._read_varint(data, 1)
+        body = data[at:]
+        info = self._gather_lists((nb, len(body)))
+        header = data[:1] + self._varint(sum(i[0] for i in info))
+        off = len(header) + sum(i[1] for i in info[: self.rank])
+        if self.rank == 0:
+            with open(path, "wb") as f:
+                f.write(header)
+                f.truncate(len(header) + sum(i[1] for i in info))
+        self._barrier()
+        fd = os.open(path, os.O_WRONLY)
+        try:
+            os.pwrite(fd, body, off)
+        finally:
+            os.close(fd)
+        self._barrier()
+
+    def load_from_file(self, path: str) -> "ShardedCBL":
+        """A set sharded like this one holding the file's contents: every rank keeps the buckets of its prefix range."""
+        with open(path, "rb") as f:
+            data = f.read()
+        lo, hi = self.my_prefix_range()
+        out = self._derive(self.engine.deserialize_range(data, lo, hi))
+        out.canonical = bool(data[0])
+        return out
+
+    def _barrier(self):
+        if self.world > 1:
+            if dist.get_backend(self.group) == "gloo":
+                dist.barrier(group=self.group)
+            else:
+                dist.barrier(group=self.group, device_ids=[self.device.index])
 
     # -- global scalars --------------------------------------------------------------------------
     def local_count(self) -> int:

@@ -115,6 +115,9 @@ int32_t cbl_serialize_size(cbl_t* h, size_t* out);
 int32_t cbl_serialize(cbl_t* h, uint8_t* out, size_t cap, size_t* n_out);
 /* proto supplies K / T / PREFIX_BITS / device (the reference fixes them at compile time) */
 int32_t cbl_deserialize(const cbl_t* proto, const uint8_t* data, size_t len, cbl_t** out);
+/* same, keeping only the buckets whose prefix lies in [prefix_lo, prefix_hi): one rank's share of a file when the set is
+ * sharded one process per GPU (cbl_b200/sharded.py; a cbl_create_sharded handle needs no such call) */
+int32_t cbl_deserialize_range(const cbl_t* proto, const uint8_t* data, size_t len, uint64_t prefix_lo, uint64_t prefix_hi, cbl_t** out);
 int32_t cbl_save_to_file(cbl_t* h, const char* path);
 int32_t cbl_load_from_file(const cbl_t* proto, const char* path, cbl_t** out);
 

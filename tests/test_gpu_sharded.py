@@ -64,6 +64,24 @@ WORKER = textwrap.dedent(
     got = sh.contains_seqs_dev(bd.data_ptr(), np.array([0, 200000, 500000, 650000, len(big)], dtype=np.uint64)).cpu().numpy()
     exp = np.concatenate([ref.contains_seq(big[a:b]) for a, b in ((0, 200000), (200000, 500000), (500000, 650000), (650000, len(big)))])
     assert np.array_equal(got, exp)
+    # set algebra / clone / serde of two sets sharded alike (shard-local kernels, no communication)
+    others = [np.concatenate([reads[r][50000:200000], util.random_dna(80000, seed=400 + r)]) for r in range(world)]
+    sh2 = sh._derive(type(sh.engine)(K, TB, PB, CANON, 0))
+    od = torch.from_numpy(others[rank]).to(dev)
+    sh2.insert_seqs_dev(od.data_ptr(), np.array([0, len(others[rank])], dtype=np.uint64))
+    ref2 = OracleCBL(K, TB, PB, CANON)
+    for r in range(world):
+        ref2.insert_seq(others[r])
+    W = lambda o: util.to_int_list(*o.iter_words())
+    assert (sh | sh2).words() == W(ref | ref2) and (sh & sh2).words() == W(ref & ref2)
+    assert (sh - sh2).words() == W(ref - ref2) and (sh ^ sh2).words() == W(ref ^ ref2)
+    c = sh.clone(); c ^= sh2
+    assert c.words() == W(ref ^ ref2) and c.count() == (ref ^ ref2).count() and sh.words() == W(ref)
+    path = os.path.join({tmp!r}, "sharded_gpu.cbl")
+    sh.save_to_file(path)
+    assert W(ref.deserialize(open(path, "rb").read())) == W(ref)
+    assert sh.load_from_file(path).words() == W(ref)
+    sh2.close(); c.close()
     r0 = torch.from_numpy(reads[0]).to(dev)
     if rank == 0:
         sh.remove_seqs_dev(r0.data_ptr(), np.array([0, 100000, len(reads[0])], dtype=np.uint64))
@@ -85,7 +103,7 @@ WORKER = textwrap.dedent(
                                                  (59, 128, 28, True, "peer-unfused-tight")])
 def test_sharded_two_ranks_one_gpu(tmp_path, k, tb, pb, canon, mode):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, k=k, tb=tb, pb=pb, canon=canon, mode=mode))
+    script.write_text(WORKER.format(root=ROOT, k=k, tb=tb, pb=pb, canon=canon, mode=mode, tmp=str(tmp_path)))
     port = 29900 + (os.getpid() + k) % 90
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(script)]

@@ -1,6 +1,7 @@
 """world_size-2 (and 3) gloo tests of the multi-GPU host logic in cbl_b200/sharded.py, on CPU tensors:
-prefix extraction, equal-mass splitters, routing, the all-to-all-v exchange, the answer return path
-and global count, with a stand-in engine (a Python set of words per rank fed by the CPU oracle's
+prefix extraction, equal-mass splitters, routing, the all-to-all-v exchange, the answer return path,
+global count, the shard-local set algebra (| & - ^ and assign forms, clone), iteration order and the one-file serde
+written rank after rank, with a stand-in engine (a Python set of words per rank fed by the CPU oracle's
 seq_words).  The GPU engine itself is covered by the -m gpu tests."""
 import os
 import subprocess
@@ -92,6 +93,30 @@ WORKER = textwrap.dedent(
             return flags
         def count(self):
             return len(self.words)
+        # shard-local set algebra / clone / export / serde (what ShardedCBL composes rank by rank)
+        def _with(self, words):
+            e = SetEngine(); e.words = set(words); return e
+        def setop(self, op, other):
+            a, b = self.words, other.words
+            return self._with([a | b, a & b, a - b, a ^ b][op])
+        def setop_assign(self, op, other):
+            self.words = self.setop(op, other).words
+        def clone(self):
+            return self._with(self.words)
+        def words_list(self):
+            return sorted(self.words)
+        def kmers_list(self):
+            return [self.o.recover_kmer(w) for w in sorted(self.words)]
+        def _oracle_of(self):
+            o = OracleCBL(K, TB, PB, CANON)
+            for w in self.words:
+                o.insert(self.o.recover_kmer(w))
+            return o
+        def serialize(self):
+            return self._oracle_of().serialize()
+        def deserialize_range(self, data, lo, hi):
+            sb = 2 * K + util.pos_bits(K) - PB
+            return self._with([w for w in util.to_int_list(*self.o.deserialize(data).iter_words()) if lo <= (w >> sb) < hi])
         def sample_words(self, n, seed):
             self.host["sample"] = util.random_dna(n, seed)
             return self.seq_words("sample", np.array([0, n], dtype=np.uint64))
@@ -126,6 +151,34 @@ WORKER = textwrap.dedent(
     exp = ref.contains_seq(q)
     assert np.array_equal(got, exp), "sharded contains_seq != reference answers"
     assert 0 < got.sum() < len(got)
+    # ---- set algebra between two sets sharded alike: shard-local, result = concatenation by rank (src/cbl.rs:411-569)
+    other_reads = [np.concatenate([reads[r][2000:9000], util.random_dna(6000, seed=700 + r)]) for r in range(world)]
+    sh2 = sh._derive(SetEngine())
+    sh2.engine.host["o"] = other_reads[rank]
+    sh2.insert_seqs_dev("o", np.array([0, len(other_reads[rank])], dtype=np.uint64))
+    ref2 = OracleCBL(K, TB, PB, CANON)
+    for r in range(world):
+        ref2.insert_seq(other_reads[r])
+    W = lambda o: util.to_int_list(*o.iter_words())
+    assert (sh | sh2).words() == W(ref | ref2) and (sh & sh2).words() == W(ref & ref2)
+    assert (sh - sh2).words() == W(ref - ref2) and (sh ^ sh2).words() == W(ref ^ ref2)
+    c = sh.clone(); c |= sh2; assert c.words() == W(ref | ref2)
+    c = sh.clone(); c &= sh2; assert c.words() == W(ref & ref2) and c.count() == (ref & ref2).count()
+    c = sh.clone(); c -= sh2; assert c.words() == W(ref - ref2)
+    c = sh.clone(); c ^= sh2; assert c.words() == W(ref ^ ref2)
+    assert sh.words() == W(ref), "operands untouched"
+    assert list(sh.iter()) == [ref.recover_kmer(w) for w in W(ref)], "iter: ascending word order, rank after rank"
+    try:
+        sh | ShardedCBL(K, TB, PB, CANON, engine=SetEngine(), splitters=[s + 1 for s in sh.splitters_u32.tolist()])
+        raise SystemExit("differently sharded operand accepted")
+    except ValueError:
+        pass
+    # ---- serde: ONE file in the reference's layout, written rank after rank; the oracle reads it; a sharded set reloads it
+    path = os.path.join({tmp!r}, "sharded.cbl")
+    sh.save_to_file(path)
+    assert W(ref.deserialize(open(path, "rb").read())) == W(ref), "oracle cannot read the sharded file"
+    back = sh.load_from_file(path)
+    assert back.words() == W(ref) and back.local_words() == sh.local_words()
     # remove what rank 0 inserted, everywhere
     eng.host["r0"] = reads[0]
     if rank == 0:
@@ -144,7 +197,7 @@ WORKER = textwrap.dedent(
 @pytest.mark.parametrize("world,k,tb,pb,canon", [(2, 25, 64, 24, False), (2, 59, 128, 28, True), (3, 31, 128, 24, False)])
 def test_sharded_routing_gloo(tmp_path, world, k, tb, pb, canon):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, k=k, tb=tb, pb=pb, canon=canon))
+    script.write_text(WORKER.format(root=ROOT, k=k, tb=tb, pb=pb, canon=canon, tmp=str(tmp_path)))
     port = 29600 + (os.getpid() + world * 7 + k) % 300
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(script)]
