@@ -435,22 +435,19 @@ def membership(torch, sorted_set, q):
     return res[sorted_set.shape[0] :]
 
 
-def parity_check(torch, dist, cbl, world, rank, device, k, t_bits, pb, canonical, index_dev, i_off, query_dev, q_off, answers_dev, threads,
-                 sample_records=None):
-    """(1) the WHOLE built set: oracle words of every index record (all ranks), routed to the owner rank by the shard's
-    splitters, sorted + deduplicated == the shard's stored words in ascending order (and the count);
-    (2) the step's own answers for >= 1 % of the query records (hit and miss records alike) == membership of their
-    oracle words in that oracle-derived set.  Returns a dict for the JSON line."""
-    t0 = time.perf_counter()
-    wide = (2 * k + (2 * k - 1).bit_length()) > 64
-    suffix_bits = 2 * k + (2 * k - 1).bit_length() - pb
-    h_index = index_dev.cpu().numpy()
-    n_i = len(i_off) - 1
-    parts = oracle_words(h_index, i_off, range(n_i), k, t_bits, pb, canonical, threads)
+def word_geometry(k: int, pb: int):
+    word_bits = 2 * k + (2 * k - 1).bit_length()
+    return word_bits > 64, word_bits - pb          # (128-bit device words?, SUFFIX_BITS)
+
+
+def expected_shard_set(torch, dist, cbl, world, rank, device, k, t_bits, pb, canonical, reads_dev, offsets, threads):
+    """oracle words of EVERY record of `reads_dev` (all ranks), routed to the owner rank by the shard's splitters, sorted +
+    deduplicated: the words this rank's shard must hold after insert_seq of those reads into an empty set"""
+    wide, suffix_bits = word_geometry(k, pb)
+    h = reads_dev.cpu().numpy()
+    parts = oracle_words(h, offsets, range(len(offsets) - 1), k, t_bits, pb, canonical, threads)
     mine = words_to_torch(torch, device, parts, wide)
-    del parts, h_index
-    t_words = time.perf_counter() - t0
-    local = cbl.engine.cbl if world > 1 else cbl
+    del parts, h
     if world > 1:
         sp = cbl.splitters.to(device)
         dest = torch.bucketize(word_prefix(torch, mine, suffix_bits), sp, right=True)
@@ -464,8 +461,11 @@ def parity_check(torch, dist, cbl, world, rank, device, k, t_bits, pb, canonical
         del send, mine, order, dest
     else:
         recv = mine
-    expect = sort_unique(torch, recv)
-    del recv
+    return sort_unique(torch, recv)
+
+
+def exported_shard_words(torch, local, device, wide: bool):
+    """the shard's stored words in ascending order, left on the device (int64 (n,) or (n, 2) = [lo, hi])"""
     n_loc = local.count()
     got = torch.empty((n_loc, 2) if wide else (n_loc,), dtype=torch.int64, device=device)
     torch.cuda.synchronize()
@@ -474,12 +474,33 @@ def parity_check(torch, dist, cbl, world, rank, device, k, t_bits, pb, canonical
         m = min(CH, n_loc - at)
         local.export_words_dev(at, m, got.data_ptr() + at * (16 if wide else 8))
         at += m
+    return got
+
+
+def count_set_mismatches(got, expect, wide: bool) -> int:
     if got.shape[0] == expect.shape[0]:
-        set_mismatch = int((got != expect).any(dim=1).sum().item()) if wide else int((got != expect).sum().item())
-    else:
-        m = min(got.shape[0], expect.shape[0])
-        d = (got[:m] != expect[:m])
-        set_mismatch = abs(got.shape[0] - expect.shape[0]) + int((d.any(dim=1) if wide else d).sum().item())
+        return int((got != expect).any(dim=1).sum().item()) if wide else int((got != expect).sum().item())
+    m = min(got.shape[0], expect.shape[0])
+    d = got[:m] != expect[:m]
+    return abs(got.shape[0] - expect.shape[0]) + int((d.any(dim=1) if wide else d).sum().item())
+
+
+def parity_check(torch, dist, cbl, world, rank, device, k, t_bits, pb, canonical, index_dev, i_off, query_dev, q_off, answers_dev, threads,
+                 sample_records=None):
+    """(1) the WHOLE built set: oracle words of every index record (all ranks), routed to the owner rank by the shard's
+    splitters, sorted + deduplicated == the shard's stored words in ascending order (and the count);
+    (2) the step's own answers for >= 1 % of the query records (hit and miss records alike) == membership of their
+    oracle words in that oracle-derived set.  Returns a dict for the JSON line."""
+    t0 = time.perf_counter()
+    wide, suffix_bits = word_geometry(k, pb)
+    n_i = len(i_off) - 1
+    expect = expected_shard_set(torch, dist, cbl, world, rank, device, k, t_bits, pb, canonical, index_dev, i_off, threads)
+    t_words = time.perf_counter() - t0
+    local = cbl.engine.cbl if world > 1 else cbl
+    got = exported_shard_words(torch, local, device, wide)
+    n_loc = got.shape[0]
+    set_mismatch = count_set_mismatches(got, expect, wide)
+    del got
     # ---- answers of sampled query records
     n_q = len(q_off) - 1
     if sample_records is None:
