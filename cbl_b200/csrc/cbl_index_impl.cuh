@@ -741,17 +741,119 @@ public:
             r = q;
         }
     }
+    // Host buffers, software-pipelined (src/cbl.rs:328-339 for a whole record loop, examples/cbl.rs:160-163): a batch of
+    // <= batch_kmers_ k-mers is cut into groups of ~CBL_INS_GROUP_BYTES; while the words kernel of group g runs, the reads
+    // of group g + 1 are on their way in (copy stream, two staging slots), all groups write into the batch's one sort
+    // buffer and fold their digits into its one histogram; then ONE sort + ONE merge per batch.
+    struct InSlot {
+        DevBuf<uint8_t> seq, blob;
+        HostStage stage;
+        cudaEvent_t copied = nullptr, consumed = nullptr;
+        bool used = false;
+        ~InSlot() {
+            if (copied) cudaEventDestroy(copied);
+            if (consumed) cudaEventDestroy(consumed);
+        }
+    };
     void insert_seqs(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, bool remove) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         check_records(offsets, n_seqs);
-        for_each_group(offsets, n_seqs, [&](size_t r, size_t q) {
-            const uint64_t b0 = offsets[r], nbytes = offsets[q] - b0;
-            DevBuf<uint8_t> d(nbytes + 64, st_);
-            CUDA_CHECK(cudaMemcpyAsync(d.get(), seq + b0, nbytes, cudaMemcpyHostToDevice, st_));
-            std::vector<uint64_t> off(q - r + 1);
-            for (size_t i = r; i <= q; i++) off[i - r] = offsets[i] - b0;
-            mutate_seqs_dev(d.get(), nbytes, off.data(), q - r, remove ? EDIT_DEL : EDIT_INS);
-        });
+        const int mode = remove ? EDIT_DEL : EDIT_INS;
+        last_produced = 0;
+        const uint64_t group_bytes = std::max<uint64_t>(1 << 20, env_u64("CBL_INS_GROUP_BYTES", 64ull << 20));
+        const uint32_t piece_kmers = (uint32_t)std::min<uint64_t>(PIECE_KMERS, std::max<uint64_t>(CHUNK_KMERS, (group_bytes / 4) / CHUNK_KMERS * CHUNK_KMERS));
+        PieceList pl;
+        build_pieces(offsets, 0, n_seqs, pl, piece_kmers);
+        const size_t np = pl.kmers.size();
+        cudaStream_t cs = side_[0];
+        auto piece_end = [&](size_t i) { return pl.byte_off[i] + pl.kmers[i] + (uint64_t)cfg_.k - 1; };
+        size_t p = 0;
+        while (p < np) {
+            size_t q = p;
+            uint64_t nk = 0;
+            while (q < np && (q == p || nk + pl.kmers[q] <= batch_kmers_)) { nk += pl.kmers[q]; q++; }
+            DevBuf<W> a(nk, st_), b(nk, st_);
+            const SortPlan sp = plan_sort(nk);
+            DevBuf<unsigned long long> stat, hist;
+            init_status(stat);
+            const bool fused_hist = sp.n_pass <= SW_HIST_MAX && nk > 1 && env_u64("CBL_HIST_FUSED", 1) != 0;
+            if (fused_hist) { hist.alloc((size_t)sp.n_pass * 256, st_); hist.zero(); }
+            InSlot slots[2];
+            for (auto& sl : slots) {
+                CUDA_CHECK(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming));
+            }
+            size_t g0 = p;
+            int gi = 0;
+            while (g0 < q) {
+                size_t g1 = g0;
+                while (g1 < q && (g1 == g0 || piece_end(g1) - pl.byte_off[g0] <= group_bytes)) g1++;
+                InSlot& sl = slots[gi & 1];
+                if (sl.used) CUDA_CHECK(cudaEventSynchronize(sl.consumed));   // the words kernel that read this slot is done
+                const uint64_t b0 = pl.byte_off[g0], nbytes = piece_end(g1 - 1) - b0;
+                const size_t m = g1 - g0;
+                const size_t o_out = m * 8, o_ch = 2 * m * 8, o_km = (3 * m + 1) * 8, blob_bytes = o_km + m * 4;
+                sl.stage.reserve(blob_bytes);
+                uint64_t* h_byte = reinterpret_cast<uint64_t*>(sl.stage.p);
+                uint64_t* h_out = reinterpret_cast<uint64_t*>(sl.stage.p + o_out);
+                uint64_t* h_ch = reinterpret_cast<uint64_t*>(sl.stage.p + o_ch);
+                uint32_t* h_km = reinterpret_cast<uint32_t*>(sl.stage.p + o_km);
+                for (size_t i = 0; i < m; i++) {
+                    h_byte[i] = pl.byte_off[g0 + i] - b0;
+                    h_out[i] = pl.out_off[g0 + i] - pl.out_off[p];
+                    h_ch[i] = pl.chunk0[g0 + i] - pl.chunk0[g0];
+                    h_km[i] = pl.kmers[g0 + i];
+                }
+                h_ch[m] = pl.chunk0[g1] - pl.chunk0[g0];
+                if (!sl.used || sl.seq.size() < nbytes + 64) sl.seq.alloc(std::max<uint64_t>(nbytes, group_bytes) + 64, cs);
+                sl.blob.alloc(blob_bytes, cs);
+                CUDA_CHECK(cudaMemcpyAsync(sl.seq.get(), seq + b0, nbytes, cudaMemcpyHostToDevice, cs));
+                CUDA_CHECK(cudaMemcpyAsync(sl.blob.get(), sl.stage.p, blob_bytes, cudaMemcpyHostToDevice, cs));
+                CUDA_CHECK(cudaEventRecord(sl.copied, cs));
+                SeqBatch sb;
+                sb.seq = sl.seq.get(); sb.seq_end = sl.seq.get() + nbytes;
+                sb.piece_byte = reinterpret_cast<const uint64_t*>(sl.blob.get());
+                sb.piece_out = reinterpret_cast<const uint64_t*>(sl.blob.get() + o_out);
+                sb.piece_chunk0 = reinterpret_cast<const uint64_t*>(sl.blob.get() + o_ch);
+                sb.piece_kmers = reinterpret_cast<const uint32_t*>(sl.blob.get() + o_km);
+                sb.n_pieces = (uint32_t)m; sb.n_chunks = h_ch[m];
+                CUDA_CHECK(cudaStreamWaitEvent(st_, sl.copied, 0));
+                launch_seq_words(sb, 0, false, a.get(), nullptr, stat.get() + ST_BAD_BYTE, st_, fused_hist ? hist.get() : nullptr, &sp);
+                CUDA_CHECK(cudaEventRecord(sl.consumed, st_));
+                CUDA_CHECK(cudaStreamWaitEvent(cs, sl.consumed, 0));          // the slot's buffers go back to the copy stream's arena list
+                sl.used = true;
+                g0 = g1;
+                gi++;
+            }
+            uint64_t produced = nk;
+            const bool ok = mutate_with_words(a.get(), b.get(), nk, mode, fused_hist ? hist.get() : nullptr, &stat);
+            CUDA_CHECK(cudaStreamSynchronize(cs));
+            if (!ok) {
+                // non-ACGT bytes: nothing was applied; the batch's bytes go in at once and take the sanitiser
+                const uint64_t b0 = pl.byte_off[p], nbytes = piece_end(q - 1) - b0;
+                DevBuf<uint8_t> d(nbytes + 64, st_);
+                CUDA_CHECK(cudaMemcpyAsync(d.get(), seq + b0, nbytes, cudaMemcpyHostToDevice, st_));
+                PieceList sub;
+                sub.chunk0.push_back(0);
+                for (size_t i = p; i < q; i++) {
+                    sub.byte_off.push_back(pl.byte_off[i] - b0);
+                    sub.out_off.push_back(pl.out_off[i] - pl.out_off[p]);
+                    sub.kmers.push_back(pl.kmers[i]);
+                    sub.n_chunks += div_up(pl.kmers[i], CHUNK_KMERS);
+                    sub.chunk0.push_back(sub.n_chunks);
+                }
+                sub.n_kmers = nk;
+                DevPieces dp;
+                upload_pieces(sub, 0, q - p, 0, d.get(), nbytes, dp, st_);
+                Sanitized sn;
+                sanitize_batch(dp.batch, sn, st_);
+                produced = run_seq_words(sn.dp.batch, sn.n_kmers, 0, false, a.get(), nullptr, st_);
+                mutate_with_words(a.get(), b.get(), produced, mode);
+            }
+            last_produced += produced;
+            p = q;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(st_));
     }
     // Host buffers -> answers on the host, software-pipelined over N_SLOTS streams: while one group's
     // kernel runs, the next group's reads are on their way in and the previous group's answers on

@@ -430,7 +430,10 @@ class ShardedCBL:
     # for the same SM resources when co-resident (each slows down by what the other takes), so the default is 1.
     PIPE = 1
 
-    FUSED = 1   # CBL_FUSED=0: route kernel, count exchange, probe kernel one after the other (the round-1 path)
+    # CBL_FUSED=1 selects the producer + consumer kernels with block signalling; measured on 2 x B200 (bench.py, 1 Gbp per
+    # rank): 46.0 ms per step against 39.9 ms for route kernel -> count exchange -> one probe launch: co-resident, the two
+    # kernels are both bound by instruction issue and the capped grids cost occupancy
+    FUSED = 0
 
     def _peer_contains_fused(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
         """contains_seq of this rank's reads as ONE producer + ONE consumer kernel per rank (cbl_seq_contains_fused_dev): words
@@ -501,9 +504,15 @@ class ShardedCBL:
         for i in range(1, len(cuts)):
             cuts[i] = max(cuts[i], cuts[i - 1])
         sub_n = [int(csum[cuts[b + 1]] - csum[cuts[b]]) for b in range(pipe)]
-        # doubles as the barrier "every rank is done with the buffers of the previous call"
-        n_max = int(px.all_counts(np.array([max(sub_n)], dtype=np.uint64)).max())
-        cap = int(n_max / self.world * float(os.environ.get("CBL_ROUTE_SLACK", self.SLACK))) + 4096
+        # Region sizing needs one exchange on the first call only: later calls start from the capacity they find (a region
+        # that turns out too small is detected by the count exchange after the route and everybody retries).  No barrier
+        # is needed here: the previous call ended with "all answers have landed" and every rank gathered its own answers
+        # before it could enter this call's first collective.
+        if px.cap == 0:
+            n_max = int(px.all_counts(np.array([max(sub_n)], dtype=np.uint64)).max())
+            cap = int(n_max / self.world * float(os.environ.get("CBL_ROUTE_SLACK", self.SLACK))) + 4096
+        else:
+            cap = px.cap
         mark("plan + first count exchange")
         out = torch.empty(total, dtype=torch.uint8, device=self.device)
         torch.cuda.current_stream(self.device).synchronize()
@@ -584,13 +593,60 @@ class ShardedCBL:
         t = torch.from_numpy(np.ascontiguousarray(buf)).to(self.device, non_blocking=True)
         self.remove_seqs_dev(t.data_ptr(), offsets)
 
+    E2E_PIPE = 4   # sub-batches of a host-buffer query (CBL_E2E_PIPE); must be the same on every rank
+
     def contains_seqs(self, buf: np.ndarray, offsets: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
-        t = torch.from_numpy(np.ascontiguousarray(buf)).to(self.device, non_blocking=True)
-        ans = self.contains_seqs_dev(t.data_ptr(), offsets)
+        """Host buffers in, answers on the host (what a user of the reference calls), software-pipelined: the reads are cut
+        into sub-batches of whole records; while sub-batch b is routed / probed, the reads of b + 1 .. are on their way in
+        and the answers of b - 1 on their way out (H2D and D2H on their own streams and copy engines; true DMA when the
+        caller's buffers are pinned).  Every rank must use the same number of sub-batches (the collectives pair up)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_rec = len(offsets) - 1
+        kpr = np.array([max(int(offsets[i + 1] - offsets[i]) - self.k + 1, 0) for i in range(n_rec)], dtype=np.int64)
+        total = int(kpr.sum())
         if out is None:
-            return ans.cpu().numpy()
-        torch.from_numpy(out)[: ans.numel()].copy_(ans)
-        return out[: ans.numel()]
+            out = np.empty(max(total, 1), dtype=np.uint8)
+        if self.device.type != "cuda":      # stand-in engines (CPU tests): plain path
+            t = torch.from_numpy(np.ascontiguousarray(buf))
+            ans = self.contains_seqs_dev(t.data_ptr() if hasattr(t, "data_ptr") else t, offsets)
+            torch.from_numpy(out)[: ans.numel()].copy_(ans)
+            return out[: ans.numel()]
+        pipe = max(1, int(os.environ.get("CBL_E2E_PIPE", self.E2E_PIPE)))
+        csum = np.concatenate([[0], np.cumsum(kpr)])
+        cuts = [int(np.searchsorted(csum, total * b / pipe, side="left")) for b in range(pipe)] + [n_rec]
+        cuts = [min(max(c, 0), n_rec) for c in cuts]
+        for i in range(1, len(cuts)):
+            cuts[i] = max(cuts[i], cuts[i - 1])
+        h_in, h_out = torch.from_numpy(np.ascontiguousarray(buf)), torch.from_numpy(out)
+        if getattr(self, "_copy_streams", None) is None:
+            self._copy_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        s_in, s_out = self._copy_streams
+        cur = torch.cuda.current_stream(self.device)
+        d_in, ev_in = [], []
+        for b in range(pipe):
+            b0, b1 = int(offsets[cuts[b]]), int(offsets[cuts[b + 1]])
+            d_in.append(torch.empty(max(b1 - b0, 1), dtype=torch.uint8, device=self.device))
+        s_in.wait_stream(cur)
+        with torch.cuda.stream(s_in):
+            for b in range(pipe):
+                b0, b1 = int(offsets[cuts[b]]), int(offsets[cuts[b + 1]])
+                if b1 > b0:
+                    d_in[b][: b1 - b0].copy_(h_in[b0:b1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                ev_in.append(ev)
+        keep = []
+        for b in range(pipe):
+            ev_in[b].synchronize()
+            sub_off = offsets[cuts[b] : cuts[b + 1] + 1] - offsets[cuts[b]]
+            ans = self.contains_seqs_dev(d_in[b].data_ptr(), sub_off)        # host-synchronous: the answers are complete
+            k0 = int(csum[cuts[b]])
+            if ans.numel():
+                with torch.cuda.stream(s_out):
+                    h_out[k0 : k0 + ans.numel()].copy_(ans, non_blocking=True)
+            keep.append(ans)
+        s_out.synchronize()
+        return out[:total]
 
     # -- set algebra, clone, iteration, serde: shard-local, composed in rank order (src/cbl.rs:411-569, 358-360, 127-160) ----
     def _derive(self, engine) -> "ShardedCBL":

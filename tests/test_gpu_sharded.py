@@ -1,7 +1,8 @@
 """The sharded GPU path end to end on ONE device: two processes share cuda:0, the control plane (count
 matrix, IPC handles, barriers) runs over gloo and the data path is the fused route + peer-memory exchange
-(CUDA IPC mappings of the other process's buffers; default query = producer + consumer kernels with block signalling
-through peer memory, cbl_seq_contains_fused_dev), checked bit-exactly against the oracle.  The same code
+(CUDA IPC mappings of the other process's buffers; the query runs as route kernel -> count exchange -> one probe launch,
+or, "fused" modes, as producer + consumer kernels with block signalling through peer memory), checked bit-exactly
+against the oracle.  The same code
 runs one process per GPU over NVLink on a multi-GPU box (bench.py --gpus N)."""
 import os
 import subprocess
@@ -27,8 +28,9 @@ WORKER = textwrap.dedent(
         os.environ["CBL_ROUTE_SLACK"] = "0.7"
     if "pipe" in MODE:    # pipelined query: 3 sub-batches, route of b + 1 overlapping the probe of b, two buffer sets
         os.environ["CBL_PIPE"] = "3"
-    if "pipe" in MODE or "unfused" in MODE:   # the round-1 query path: route kernel, count exchange, probe kernel in turn
-        os.environ["CBL_FUSED"] = "0"
+    # default query path: route kernel, count exchange, ONE probe launch; "fused": producer + consumer kernels with block
+    # signalling through peer memory (cbl_seq_contains_fused_dev)
+    os.environ["CBL_FUSED"] = "1" if "fused" in MODE else "0"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     torch.cuda.set_device(0)
@@ -99,8 +101,8 @@ WORKER = textwrap.dedent(
 @pytest.mark.gpu
 @pytest.mark.parametrize("k,tb,pb,canon,mode", [(25, 64, 24, False, "peer"), (31, 128, 24, True, "peer"), (59, 128, 28, False, "peer"),
                                                  (25, 64, 24, True, "peer-tight"), (25, 64, 24, False, "peer-pipe"),
-                                                 (31, 128, 24, True, "peer-pipe-tight"), (25, 64, 24, True, "peer-unfused"),
-                                                 (59, 128, 28, True, "peer-unfused-tight")])
+                                                 (31, 128, 24, True, "peer-pipe-tight"), (25, 64, 24, True, "peer-fused"),
+                                                 (59, 128, 28, True, "peer-fused-tight"), (31, 128, 24, False, "peer-fused")])
 def test_sharded_two_ranks_one_gpu(tmp_path, k, tb, pb, canon, mode):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT, k=k, tb=tb, pb=pb, canon=canon, mode=mode, tmp=str(tmp_path)))
