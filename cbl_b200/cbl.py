@@ -398,6 +398,52 @@ class CBL:
     def prefix_load(self) -> float:
         return self.num_buckets() / float(1 << self.prefix_bits)  # src/wordset/mod.rs:254-256
 
+    def buckets_size_count(self) -> dict:
+        """bucket size -> number of buckets of that size (src/cbl.rs:374-377, src/wordset/mod.rs:265-271)"""
+        _, s = self.buckets_sizes()
+        sizes, counts = np.unique(s, return_counts=True)
+        return {int(a): int(b) for a, b in zip(sizes, counts)}
+
+    def buckets_load_repartition(self) -> dict:
+        """bucket size -> share of the stored k-mers held by buckets of that size (src/wordset/mod.rs:273-280)"""
+        sc = self.buckets_size_count()
+        total = float(sum(k * v for k, v in sc.items())) or 1.0
+        return {k: k * v / total for k, v in sc.items()}
+
+    TRIE_THRESHOLD = 1024   # src/wordset/mod.rs:34: a bucket becomes a byte trie above this many suffixes
+
+    def buckets_nodes(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(prefix, node count) per bucket as the reference would report it (src/wordset/mod.rs:282-287): a Vec bucket
+        counts its elements (src/trievec/mod.rs:37-42), a bucket above the trie threshold counts the nodes of the 256-ary byte
+        trie over its big-endian suffixes (src/trie.rs:90-102) = 1 + the number of distinct d-byte heads for d < BYTES —
+        a pure function of the bucket's contents, computed here from the sorted suffixes (the GPU keeps no trie)."""
+        p, s = self.buckets_sizes()
+        nodes = s.astype(np.uint64).copy()
+        big = np.flatnonzero(s > self.TRIE_THRESHOLD)
+        if len(big):
+            kbits = 2 * self.k
+            pos_bits = (kbits - 1).bit_length()
+            suffix_bits = kbits + pos_bits - self.prefix_bits
+            nbytes = (suffix_bits + 7) // 8
+            starts = np.concatenate([[0], np.cumsum(s.astype(np.int64))])
+            lo = np.zeros(int(s.max()), dtype=np.uint64)
+            hi = np.zeros_like(lo)
+            n = C.c_size_t()
+            for b in big:
+                self._chk(self._L.cbl_export_words(self._h, int(starts[b]), lo.ctypes.data_as(u64p), hi.ctypes.data_as(u64p), int(s[b]), C.byref(n)))
+                suf = [(int(a) | (int(h) << 64)) & ((1 << suffix_bits) - 1) for a, h in zip(lo[: n.value], hi[: n.value])]
+                total = 1
+                for d in range(1, nbytes):
+                    total += len({x >> (8 * (nbytes - d)) for x in suf})
+                nodes[b] = total
+        return p, nodes
+
+    def buckets_node_count(self) -> dict:
+        """node count -> number of buckets with that many nodes (src/cbl.rs:392-396)"""
+        _, n = self.buckets_nodes()
+        v, c = np.unique(n, return_counts=True)
+        return {int(a): int(b) for a, b in zip(v, c)}
+
     # -- set operations (src/cbl.rs:411-569, 108-124) --------------------------------------------
     def _binary(self, op: int, other: "CBL") -> "CBL":
         h = C.c_void_p()

@@ -1,4 +1,5 @@
 // extern "C" surface of libcbl_gpu (include/cbl_gpu.h).  Nothing but status codes crosses the ABI.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -169,12 +170,38 @@ cbl_handle* deserialize_index(const cbl_handle* proto, const uint8_t* data, size
     return h.release();
 }
 
+// k-way union / intersection (src/cbl.rs:108-124, src/wordset/set_ops.rs:11-75).  Every binary step is one streaming merge
+// of two CSR indexes, so the order matters for traffic: unions pair the inputs up in a balanced tree (every element is
+// rewritten ~log2 k times instead of up to k times by a left fold), intersections start from the two smallest sets (the
+// running result only shrinks).
 cbl_handle* fold_many(cbl_handle** hs, size_t n, int op) {
     if (!hs || n == 0) throw Error(CBL_EINVAL, "empty list of indexes");
     for (size_t i = 0; i < n; i++) need(hs[i], "index handle");
+    std::vector<std::unique_ptr<IIndex>> own;      // intermediate results
+    std::vector<IIndex*> cur;
+    for (size_t i = 0; i < n; i++) cur.push_back(hs[i]->ix.get());
+    if (n == 1) { own.emplace_back(cur[0]->clone()); cur[0] = own.back().get(); }
+    if (op == SETOP_AND) {
+        std::stable_sort(cur.begin(), cur.end(), [](IIndex* a, IIndex* b) { return a->count() < b->count(); });
+        own.emplace_back(cur[0]->setop(op, cur[1 < n ? 1 : 0]));
+        IIndex* acc = own.back().get();
+        for (size_t i = 2; i < n; i++) acc->setop_assign(op, cur[i]);
+        cur.assign(1, acc);
+    }
+    while (cur.size() > 1) {
+        std::vector<IIndex*> next;
+        for (size_t i = 0; i + 1 < cur.size(); i += 2) {
+            own.emplace_back(cur[i]->setop(op, cur[i + 1]));
+            next.push_back(own.back().get());
+        }
+        if (cur.size() & 1) next.push_back(cur.back());
+        cur.swap(next);
+    }
+    // hand the final result over (it is owned by `own` unless n == 1 cloned it there too)
     std::unique_ptr<cbl_handle> acc(new cbl_handle());
-    acc->ix.reset(hs[0]->ix->clone());
-    for (size_t i = 1; i < n; i++) acc->ix->setop_assign(op, hs[i]->ix.get());
+    for (auto& o : own)
+        if (o.get() == cur[0]) { acc->ix = std::move(o); break; }
+    if (!acc->ix) acc->ix.reset(cur[0]->clone());
     return acc.release();
 }
 }  // namespace

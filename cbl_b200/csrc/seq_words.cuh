@@ -163,8 +163,13 @@ __global__ void __launch_bounds__(SW_THREADS, ((MODE == 3 || MODE == 4) && U == 
     __shared__ uint16_t s_dr[RN], s_inv[RN];
     __shared__ uint32_t s_cnt[16], s_off[17], s_base[16];
     __shared__ W* s_peer[16];
+    __shared__ uint32_t s_split[16];   // MODE 2: the splitters (unused ones 0xFFFFFFFF), searched by bisection
     if (MODE == 2) {
-        if (threadIdx.x < 16) { s_cnt[threadIdx.x] = 0; s_peer[threadIdx.x] = sa.peer[threadIdx.x]; }
+        if (threadIdx.x < 16) {
+            s_cnt[threadIdx.x] = 0;
+            s_peer[threadIdx.x] = sa.peer[threadIdx.x];
+            s_split[threadIdx.x] = threadIdx.x < ROUTE_MAX_SPLIT ? sa.dest.split[threadIdx.x] : 0xFFFFFFFFu;
+        }
         __syncthreads();
     }
     __shared__ uint32_t s_fwd[2][32];
@@ -388,7 +393,13 @@ __global__ void __launch_bounds__(SW_THREADS, ((MODE == 3 || MODE == 4) && U == 
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     if (active[u]) {
-                        const uint32_t d = sa.dest(word[u]);
+                        // owner = number of splitters <= prefix: 4 bisection steps over the 15 (padded) splitters in shared
+                        // memory instead of 15 compares against kernel parameters
+                        const uint32_t pfx = (uint32_t)(word[u] >> sa.dest.suffix_bits);
+                        uint32_t d = s_split[7] <= pfx ? 8u : 0u;
+                        d += s_split[d + 3] <= pfx ? 4u : 0u;
+                        d += s_split[d + 1] <= pfx ? 2u : 0u;
+                        d += s_split[d] <= pfx ? 1u : 0u;
                         const uint32_t r = atomicAdd(&s_cnt[d], 1u);   // rank among the chunk's words for owner d
                         s_stage[slot[u]] = word[u];
                         s_dr[slot[u]] = (uint16_t)((d << 11) | r);
@@ -479,9 +490,10 @@ __global__ void __launch_bounds__(SW_THREADS, ((MODE == 3 || MODE == 4) && U == 
             __syncthreads();
             // owner order: consecutive q of one owner -> consecutive addresses in its region (coalesced NVLink stores)
             for (int q = threadIdx.x; q < m; q += SW_THREADS) {
-                uint32_t d = 0;
-#pragma unroll
-                for (int t = 1; t < 16; t++) d += s_off[t] <= (uint32_t)q;
+                uint32_t d = s_off[8] <= (uint32_t)q ? 8u : 0u;   // owner of output slot q: largest d with s_off[d] <= q (bisection)
+                d += s_off[d + 4] <= (uint32_t)q ? 4u : 0u;
+                d += s_off[d + 2] <= (uint32_t)q ? 2u : 0u;
+                d += s_off[d + 1] <= (uint32_t)q ? 1u : 0u;
                 const uint32_t bd = s_base[d];
                 if (bd != 0xFFFFFFFFu) s_peer[d][(size_t)bd + ((uint32_t)q - s_off[d])] = s_stage[s_inv[q]];
             }

@@ -5,6 +5,7 @@
 // is the compiled-language host side above the boundary; INTEGRATION.md shows the Rust binding.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -110,6 +111,20 @@ public:
         if (n) chk(cbl_bucket_sizes(h_, p.data(), s.data(), n, &n));
         std::vector<std::pair<size_t, size_t>> r(n);
         for (size_t i = 0; i < n; i++) r[i] = {p[i], s[i]};
+        return r;
+    }
+    // src/cbl.rs:374-396: bucket size -> number of buckets / share of the stored k-mers
+    std::map<size_t, size_t> buckets_size_count() const {
+        std::map<size_t, size_t> m;
+        for (auto& ps : buckets_sizes()) m[ps.second]++;
+        return m;
+    }
+    std::map<size_t, double> buckets_load_repartition() const {
+        const auto sc = buckets_size_count();
+        double total = 0;
+        for (auto& kv : sc) total += (double)(kv.first * kv.second);
+        std::map<size_t, double> r;
+        for (auto& kv : sc) r[kv.first] = total > 0 ? (double)(kv.first * kv.second) / total : 0.0;
         return r;
     }
     double prefix_load() const { uint64_t nb; chk(cbl_num_buckets(h_, &nb)); return (double)nb / (double)(1ull << PREFIX_BITS); }

@@ -255,6 +255,63 @@ def test_multi_merge_intersect(gpu, orc):
         os_.append(o)
     assert_same(gpu.CBL.merge(gs).words(), ints(*orc.OracleCBL.merge(os_).iter_words()), "k-way merge")
     assert_same(gpu.CBL.intersect(gs).words(), ints(*orc.OracleCBL.intersect(os_).iter_words()), "k-way intersect")
+    # odd number of inputs of very different sizes (balanced-tree union, smallest-first intersection), one input, K=25
+    k, tb, pb = 25, 64, 24
+    base = util.random_dna(60000, 43)
+    cuts = [(0, 60000), (100, 30100), (25000, 26000), (5000, 50000), (20000, 45000)]
+    gs, os_ = [], []
+    for a, b in cuts:
+        g, o = gpu.CBL(k, tb, pb), orc.OracleCBL(k, tb, pb)
+        g.insert_seq(base[a:b])
+        o.insert_seq(base[a:b])
+        gs.append(g)
+        os_.append(o)
+    assert_same(gpu.CBL.merge(gs).words(), ints(*orc.OracleCBL.merge(os_).iter_words()), "5-way merge")
+    assert_same(gpu.CBL.intersect(gs).words(), ints(*orc.OracleCBL.intersect(os_).iter_words()), "5-way intersect")
+    assert_same(gpu.CBL.merge(gs[:1]).words(), ints(*os_[0].iter_words()), "1-way merge")
+    assert_same(gpu.CBL.intersect(gs[2:3]).words(), ints(*os_[2].iter_words()), "1-way intersect")
+    assert_same(gs[0].words(), ints(*os_[0].iter_words()), "inputs untouched")
+
+
+def test_stats_api(gpu, orc):
+    """prefix_load / buckets_sizes / buckets_size_count / buckets_load_repartition / buckets_nodes / buckets_node_count
+    (src/cbl.rs:364-396, src/wordset/mod.rs:254-295) against the same arithmetic on the oracle's bucket list; node counts of
+    buckets above the trie threshold against a plain-Python byte trie."""
+    k, tb, pb = 11, 32, 6          # 64 prefixes, necklace skew => several buckets far above 1024 suffixes
+    g, o = gpu.CBL(k, tb, pb), orc.OracleCBL(k, tb, pb)
+    seq = util.random_dna(200000, 77)
+    g.insert_seq(seq)
+    o.insert_seq(seq)
+    op, osz = o.bucket_sizes()
+    order = np.argsort(op, kind="stable")
+    op, osz = op[order], osz[order]
+    assert g.prefix_load() == len(op) / float(1 << pb)
+    sc = {}
+    for s_ in osz:
+        sc[int(s_)] = sc.get(int(s_), 0) + 1
+    assert g.buckets_size_count() == sc
+    total = float(sum(a * b for a, b in sc.items()))
+    rep = g.buckets_load_repartition()
+    assert set(rep) == set(sc) and all(abs(rep[a] - a * b / total) < 1e-12 for a, b in sc.items())
+    gp, gn = g.buckets_nodes()
+    assert np.array_equal(gp.astype(np.uint64), op)
+    sb = 2 * k + util.pos_bits(k) - pb
+    nbytes = (sb + 7) // 8
+    words = ints(*o.iter_words())
+    assert max(osz) > g.TRIE_THRESHOLD
+    for prefix, size, nodes in zip(op, osz, gn):
+        if size <= g.TRIE_THRESHOLD:
+            assert nodes == size
+        else:
+            suf = [w & ((1 << sb) - 1) for w in words if (w >> sb) == int(prefix)]
+            trie = {(): None}
+            for x in suf:
+                bs = x.to_bytes(nbytes, "big")
+                for d in range(1, nbytes):
+                    trie[bs[:d]] = None
+            assert nodes == len(trie), (int(prefix), int(size))
+    nc = g.buckets_node_count()
+    assert sum(nc.values()) == len(op)
 
 
 # ------------------------------------------------------------------------------------------------
