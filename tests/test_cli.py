@@ -44,7 +44,7 @@ def test_fastx_reader(tmp_path):
         assert list(cli.read_fastx(p)) == recs, p
     buf, off = next(cli.batches(fa))
     assert buf.tobytes() == b"".join(recs) and off.tolist() == np.concatenate([[0], np.cumsum([len(r) for r in recs])]).tolist()
-    assert cli.t_bits_for(15) == 32 and cli.t_bits_for(25) == 64 and cli.t_bits_for(29) == 64 and cli.t_bits_for(31) == 128 and cli.t_bits_for(59) == 128
+    assert cli.t_bits_for(13) == 32 and cli.t_bits_for(15) == 64 and cli.t_bits_for(25) == 64 and cli.t_bits_for(29) == 64 and cli.t_bits_for(31) == 128 and cli.t_bits_for(59) == 128
     assert cli.kmer_to_nucs(0b00_01_10_11, 4) == b"ACTG"
     with pytest.raises(SystemExit, match="Failed to open"):
         list(cli.read_fastx(str(tmp_path / "missing.fa")))
