@@ -157,17 +157,18 @@ public:
                     CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
                     CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 };
+                constexpr size_t MG_DYN = (size_t)MgCfg<W>::SMEM_ELEMS * sizeof(W) + 1024;
                 opt_in(radix_pass_kernel<W, false, ByteDigit<W>>, 96 * 1024);
                 opt_in(radix_pass_kernel<W, false, DestDigit<W>>, 96 * 1024);
                 opt_in(radix_pass_kernel<W, false, DestDigit<W>, true>, 96 * 1024);
                 opt_in(seg_sort_kernel<W, true>, SsTile<W>::SMEM);
                 opt_in(seg_sort_kernel<W, false>, SsTile<W>::SMEM);
-                opt_in(merge_apply_kernel<W, Suf, MERGE_OR, false>, 64 * 1024);
-                opt_in(merge_apply_kernel<W, Suf, MERGE_SUB, false>, 64 * 1024);
-                opt_in(merge_apply_kernel<W, Suf, MERGE_OR, true>, 64 * 1024);
-                opt_in(merge_apply_kernel<W, Suf, MERGE_AND, true>, 64 * 1024);
-                opt_in(merge_apply_kernel<W, Suf, MERGE_SUB, true>, 64 * 1024);
-                opt_in(merge_apply_kernel<W, Suf, MERGE_XOR, true>, 64 * 1024);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_OR, false>, MG_DYN);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_SUB, false>, MG_DYN);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_OR, true>, MG_DYN);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_AND, true>, MG_DYN);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_SUB, true>, MG_DYN);
+                opt_in(merge_apply_kernel<W, Suf, MERGE_XOR, true>, MG_DYN);
                 done.insert(cfg.device);
             }
         }
@@ -542,7 +543,7 @@ public:
     template <bool BCSR> void launch_merge_apply(int op, unsigned tiles, const IndexView<Suf>& v, const MergeB<W, Suf, BCSR>& B, const uint32_t* part_i,
                                                  const uint32_t* part_r, const uint32_t* part_rb, Suf* suf_out, uint32_t* cnt, uint64_t* status,
                                                  uint32_t* counter, unsigned long long* n_out, const unsigned long long* skip) {
-        const size_t smem = (size_t)MG_SMEM_ELEMS * sizeof(W);
+        const size_t smem = (size_t)MgCfg<W>::SMEM_ELEMS * sizeof(W);
 #define CBL_MERGE_CASE(OP) \
     CBL_LAUNCH((merge_apply_kernel<W, Suf, OP, BCSR>), tiles, MG_THREADS, smem, st_, v, P_, B, part_i, part_r, part_rb, suf_out, cnt, status, counter, n_out, skip)
         if constexpr (BCSR) {
@@ -576,7 +577,7 @@ public:
             return;
         }
         const IndexView<Suf> v = view();
-        const uint64_t tiles = div_up(V, MG_TILE);
+        const uint64_t tiles = div_up(V, MgCfg<W>::TILE);
         DevBuf<uint32_t> part_i(tiles + 1, st_), part_r(tiles + 1, st_), part_rb(BCSR ? tiles + 1 : 1, st_);
         CBL_LAUNCH((merge_partition_kernel<W, Suf, BCSR>), (unsigned)div_up(tiles + 1, 128), 128, 0, st_, v, P_, B, tiles, part_i.get(), part_r.get(), part_rb.get(),
                    (const unsigned long long*)(dstat + ST_SORT_FAIL));

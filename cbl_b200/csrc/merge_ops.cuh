@@ -24,10 +24,17 @@ namespace cbl {
 
 constexpr int MG_THREADS = 256;
 #ifndef CBL_MG_ITEMS
-#define CBL_MG_ITEMS 12   // measured on B200 (500 M batch words, u64): 8 -> 3.22 ms, 10 -> 2.97, 11 -> 3.30, 12 -> 2.88, 16 -> 3.66
+#define CBL_MG_ITEMS 12   // 8-byte words, measured on B200 (500 M batch words): 8 -> 3.22 ms, 10 -> 2.97, 11 -> 3.30, 12 -> 2.88, 16 -> 3.66
 #endif
-constexpr int MG_ITEMS = CBL_MG_ITEMS;
-constexpr int MG_TILE = MG_THREADS * MG_ITEMS;
+#ifndef CBL_MG_ITEMS16
+#define CBL_MG_ITEMS16 12  // 16-byte words: the tile's staging area is twice as large (occupancy), see DESIGN.md section 4
+#endif
+// elements per thread / per tile / staged words, by word width
+template <class W> struct MgCfg {
+    static constexpr int ITEMS = sizeof(W) == 8 ? CBL_MG_ITEMS : CBL_MG_ITEMS16;
+    static constexpr int TILE = MG_THREADS * ITEMS;
+    static constexpr int SMEM_ELEMS = TILE + 2 + TILE / 32 + 2;   // staging words (also holds the padded output)
+};
 
 enum : int { MERGE_OR = 0, MERGE_AND = 1, MERGE_SUB = 2, MERGE_XOR = 3 };  // same numbering as SetOp
 
@@ -80,7 +87,7 @@ __global__ void merge_partition_kernel(IndexView<Suf> ix, KParams P, MergeB<W, S
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > tiles) return;
     const uint64_t nA = ix.n, nB = B.size();
-    const uint64_t D = min(t * (uint64_t)MG_TILE, nA + nB);
+    const uint64_t D = min(t * (uint64_t)MgCfg<W>::TILE, nA + nB);
     uint64_t lo = D > nB ? D - nB : 0, hi = min(D, nA);
     while (lo < hi) {
         const uint64_t mid = (lo + hi) >> 1;
@@ -125,7 +132,6 @@ __device__ __forceinline__ void stage_csr_words(const IndexView<Suf>& ix, const 
 // shared-memory slot of output element k: one pad word per 32 elements makes the "8 consecutive elements
 // per thread" write pattern bank-conflict free while keeping the sequential read-out conflict free
 __device__ __forceinline__ uint32_t mg_pad(uint32_t k) { return k + (k >> 5); }
-constexpr int MG_SMEM_ELEMS = MG_TILE + 2 + MG_TILE / 32 + 2;   // staging words (also holds the padded output)
 
 template <class W, class Suf, int OP, bool BCSR>
 __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> ix, KParams P, MergeB<W, Suf, BCSR> B,
@@ -139,8 +145,8 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     extern __shared__ __align__(16) unsigned char mg_smem[];
     W* sK = reinterpret_cast<W*>(mg_smem);                 // [0] A halo, [1, na] A, (na, na + nb] B, [na + nb + 1] B halo
     Suf* s_out = reinterpret_cast<Suf*>(mg_smem);          // after the merge: emitted suffixes (padded slots)
-    __shared__ uint16_t s_pos[MG_TILE + 1];                // first: bucket starts inside the tile; later: run heads
-    __shared__ uint32_t s_pfx[MG_TILE + 1];                // first: prefix of those buckets;       later: prefix of the heads
+    __shared__ uint16_t s_pos[MgCfg<W>::TILE + 1];                // first: bucket starts inside the tile; later: run heads
+    __shared__ uint32_t s_pfx[MgCfg<W>::TILE + 1];                // first: prefix of those buckets;       later: prefix of the heads
     __shared__ uint32_t s_last[MG_THREADS / 32];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_excl;
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
 
     const uint32_t tile = block_ticket(tile_counter, &s_tile);
     const uint64_t nA = ix.n, nB = B.size();
-    const uint64_t D0 = min((uint64_t)tile * MG_TILE, nA + nB), D1 = min((uint64_t)(tile + 1) * MG_TILE, nA + nB);
+    const uint64_t D0 = min((uint64_t)tile * MgCfg<W>::TILE, nA + nB), D1 = min((uint64_t)(tile + 1) * MgCfg<W>::TILE, nA + nB);
     const uint32_t i0 = part_i[tile], i1 = part_i[tile + 1];
     const uint64_t j0 = D0 - i0, j1 = D1 - i1;
     const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
@@ -178,17 +184,17 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     }
     __syncthreads();
 
-    // ---- per-thread merge-path split inside the tile, then MG_ITEMS serial steps ----
+    // ---- per-thread merge-path split inside the tile, then MgCfg<W>::ITEMS serial steps ----
     const W* sA = sK + 1;
     const W* sB = sK + 1 + na;
-    const int d = min((int)threadIdx.x * MG_ITEMS, na + nb);
+    const int d = min((int)threadIdx.x * MgCfg<W>::ITEMS, na + nb);
     int lo = max(0, d - nb), hi = min(d, na);
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (sA[mid] <= sB[d - 1 - mid]) lo = mid + 1; else hi = mid;
     }
     int ia = lo, ib = d - lo;
-    W out[MG_ITEMS];
+    W out[MgCfg<W>::ITEMS];
     uint32_t emit_mask = 0;
     {
         // the current and the previous element of both sides live in registers: one shared load per step
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
         W pa = sA[ia - 1];                             // the largest A element taken so far (A halo when ia == 0)
         W pb = ib > 0 ? sB[ib - 1] : s_bprev;          // a B element equal to its predecessor is a repeat
 #pragma unroll
-        for (int e = 0; e < MG_ITEMS; e++) {
+        for (int e = 0; e < MgCfg<W>::ITEMS; e++) {
             out[e] = 0;
             if (ia + ib < na + nb) {
                 const bool take_a = ia < na && (ib >= nb || a <= b);
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     // ---- prefix runs: a head is an emitted element whose prefix differs from the previously emitted one ----
     uint32_t last = NONE;
 #pragma unroll
-    for (int e = 0; e < MG_ITEMS; e++)
+    for (int e = 0; e < MgCfg<W>::ITEMS; e++)
         if ((emit_mask >> e) & 1u) last = (uint32_t)(out[e] >> P.suffix_bits);
     // prev = prefix of the element emitted last before this thread's range ("last defined value" scan)
     uint32_t incl = last;
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     for (int w = (int)(threadIdx.x >> 5) - 1; w >= 0 && prev == NONE; w--) prev = s_last[w];
     uint32_t hm = 0;
 #pragma unroll
-    for (int e = 0; e < MG_ITEMS; e++)
+    for (int e = 0; e < MgCfg<W>::ITEMS; e++)
         if ((emit_mask >> e) & 1u) {
             const uint32_t p = (uint32_t)(out[e] >> P.suffix_bits);
             if (p != prev) hm |= 1u << e;
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
     {
         uint32_t k = off;
 #pragma unroll
-        for (int e = 0; e < MG_ITEMS; e++)
+        for (int e = 0; e < MgCfg<W>::ITEMS; e++)
             if ((emit_mask >> e) & 1u) {
                 s_out[mg_pad(k)] = (Suf)(out[e] & low_mask<W>(P.suffix_bits));
                 if ((hm >> e) & 1u) { s_pos[hoff] = (uint16_t)k; s_pfx[hoff] = (uint32_t)(out[e] >> P.suffix_bits); hoff++; }

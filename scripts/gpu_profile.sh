@@ -6,7 +6,7 @@ TAG=${1:-r01}; shift || true
 LIST=1
 if [ "${1:-}" = "--no-list" ]; then LIST=0; shift; fi
 mkdir -p gpurun_out
-B="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
+B="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-parity ${PROFILE_BENCH_ARGS:-}"
 if [ $LIST = 1 ]; then
   # (1) every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_${TAG}.csv $B > gpurun_out/launches_${TAG}.out 2>&1
