@@ -332,7 +332,7 @@ class ShardedCBL:
                 if self.rank == 0:
                     w = self.engine.sample_words(sample_bases, seed=20240229)
                     sp.copy_(equal_mass_splitters(word_prefixes(w, self.suffix_bits, prefix_bits), self.world,
-                                                   tail_cost=float(os.environ.get("CBL_SPLIT_TAIL_COST", self.TAIL_COST))))
+                                                   tail_cost=float(os.environ.get("CBL_SPLIT_TAIL_COST", self.TAIL_COST_BY_WORLD.get(self.world, self.TAIL_COST)))))
                 ctrl = sp.cpu() if dist.get_backend(group) == "gloo" else sp   # gloo: control traffic on CPU tensors
                 dist.broadcast(ctrl, src=0, group=group)
                 sp = ctrl.to(self.device)
@@ -396,10 +396,13 @@ class ShardedCBL:
                 return C, pos
             cap = int(int(C.max()) * 1.1) + 4096                     # a region overflowed somewhere: everybody retries
 
-    # relative probe cost of a word beyond the knee of the sorted prefix sample (equal_mass_splitters).  Measured with the
-    # single-launch owner-side probe on 2 x B200: 18.3 ns per 1000 words on rank 0 against 19.9 ns on rank 1 (round 1, eight
-    # launches per step: 22 vs 34 ns and the constant was 1.5)
-    TAIL_COST = 1.1
+    # Relative probe cost of a word beyond the knee of the sorted prefix sample (equal_mass_splitters).  Measured with the
+    # single-launch owner-side probe, 1 G look-ups per rank against 500 M k-mers per rank: on 8 x B200 the cost per 1000
+    # words climbs from 19.8 ns on rank 0 to 29.0 ns on ranks 5-7 (x1.5: buckets of the 4 G-k-mer set are 4x larger and the
+    # slot prediction in the structured high-prefix buckets needs more windows); on 2 x B200 it is 18.3 vs 19.9 ns (x1.1).
+    TAIL_COST_BY_WORLD = {1: 1.0, 2: 1.1, 3: 1.3}
+    TAIL_COST = 1.5
+
     SLACK = 1.3    # region capacity over the even share (cost-weighted splitters give the first rank ~20 % more words)
 
     def _mutate(self, op: int, d_buf: int, offsets: np.ndarray) -> None:
