@@ -114,17 +114,32 @@ __device__ __forceinline__ void stage_csr_words(const IndexView<Suf>& ix, const 
         }
     }
     __syncthreads();
-    int lo = 0;                                            // last bucket with start <= s; s grows, so lo never moves back
-    for (int s = threadIdx.x; s < n; s += MG_THREADS) {
-        if (lo + 1 < n_bk && (int)s_pos[lo + 1] <= s) {    // usually false: 256 elements rarely leave a bucket
-            int hi = n_bk;
-            lo++;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if ((int)s_pos[mid] <= s) lo = mid; else hi = mid;
-            }
+    // Blocked: thread t stages elements [t * per, t * per + per).  All of its suffix loads are issued before anything
+    // depends on them (the strided, one-load-per-iteration version stalled on every load: 26 % of the kernel's stall
+    // samples), its first element's bucket is found by ONE bisection of the bucket starts and the following elements walk
+    // on from there (consecutive elements rarely cross more than one bucket boundary).
+    constexpr int ITEMS = MgCfg<W>::ITEMS;
+    const int per = (n + MG_THREADS - 1) / MG_THREADS;       // <= ITEMS
+    const int s0 = (int)threadIdx.x * per, s1 = min(n, s0 + per);
+    Suf v[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
+        if (s0 + i < s1) v[i] = ix.suf[i0 + s0 + i];
+    int lo = 0;
+    if (s0 < s1) {
+        int hi = n_bk;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)s_pos[mid] <= s0) lo = mid; else hi = mid;
         }
-        dst[s] = (W)(((W)s_pfx[lo] << P.suffix_bits) | (W)ix.suf[i0 + s]);
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const int e = s0 + i;
+        if (e < s1) {
+            while (lo + 1 < n_bk && (int)s_pos[lo + 1] <= e) lo++;
+            dst[e] = (W)(((W)s_pfx[lo] << P.suffix_bits) | (W)v[i]);
+        }
     }
     __syncthreads();
 }
@@ -179,7 +194,14 @@ __global__ void __launch_bounds__(MG_THREADS) merge_apply_kernel(IndexView<Suf> 
             h = (W)(((W)ix.bucket_prefix[rp] << P.suffix_bits) | (W)ix.suf[i0 - 1]);
         }
         sK[0] = h;
-        sK[1 + na + nb] = j1 < nB ? B.at(j1, P) : SENTINEL;
+        W nxt = SENTINEL;
+        if (j1 < nB) {
+            // B[j1]: for a CSR operand its bucket is the one the partition kernel already found for this split point (a
+            // bisection of the bucket table here, by one thread with the whole CTA waiting, cost 21 dependent loads per tile)
+            if constexpr (BCSR) nxt = (W)(((W)B.ix.bucket_prefix[part_rb[tile + 1]] << P.suffix_bits) | (W)B.ix.suf[j1]);
+            else nxt = B.at(j1, P);
+        }
+        sK[1 + na + nb] = nxt;
         s_bprev = (!BCSR && j0 > 0) ? B.at(j0 - 1, P) : SENTINEL;   // an index holds no repeats
     }
     __syncthreads();
