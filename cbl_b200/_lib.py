@@ -73,7 +73,8 @@ SIGNATURES = {
     "cbl_route_counts_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, u64p]),
     "cbl_route_scatter_dev": (C.c_int32, [vp, vp, C.c_size_t, u32p, C.c_uint32, vpp, u64p, u64p, vp]),
     "cbl_seq_route_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t, u32p, C.c_uint32, vpp, C.c_uint64, vp, u64p]),
-    "cbl_seq_contains_fused_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t, u32p, C.c_uint32, vpp, vpp, vpp, C.c_uint64, vp, vpp, vpp, vpp, vpp, vp, u64p]),
+    "cbl_seq_contains_fused_dev": (C.c_int32, [vp, vp, u64p, C.c_size_t, u32p, C.c_uint32, vpp, vpp, C.c_uint64, vp, vpp, vpp, vpp, C.c_uint32, u64p]),
+    "cbl_peer_fill": (C.c_int32, [vp, vp, C.c_int32, C.c_size_t]),
     "cbl_peer_zero": (C.c_int32, [vp, vp, C.c_size_t]),
     "cbl_word_bytes": (C.c_int32, [vp, i32p]),
     "cbl_suffix_bits": (C.c_int32, [vp, i32p]),

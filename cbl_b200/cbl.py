@@ -286,10 +286,14 @@ class CBL:
     def peer_zero(self, ptr: int, nbytes: int) -> None:
         self._chk(self._L.cbl_peer_zero(self._h, ptr, nbytes))
 
-    def seq_contains_fused_dev(self, d_buf: int, offsets: np.ndarray, splitters: np.ndarray, peer_region, peer_ready, peer_final, cap: int, d_pos: int,
-                               recv_region, answer_region, ready, final_counts, ticket: int) -> np.ndarray:
-        """The fused sharded contains_seq of this rank (producer + consumer kernels over peer memory, include/cbl_gpu.h).
-        Returns the per-owner word counts (> cap = overflow)."""
+    def peer_fill(self, ptr: int, byte: int, nbytes: int) -> None:
+        self._chk(self._L.cbl_peer_fill(self._h, ptr, byte, nbytes))
+
+    def seq_contains_fused_dev(self, d_buf: int, offsets: np.ndarray, splitters: np.ndarray, peer_region, peer_final, cap: int, d_pos: int,
+                               recv_region, answer_region, final_counts, epoch: int) -> np.ndarray:
+        """The fused sharded contains_seq of this rank: one kernel whose warps alternate between routing this rank's reads and
+        probing the blocks the peers have completed here (include/cbl_gpu.h, csrc/shard_query.cuh).  Returns the per-owner
+        word counts (> cap = overflow)."""
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         sp = np.ascontiguousarray(splitters, dtype=np.uint32)
         g = len(sp) + 1
@@ -299,8 +303,8 @@ class CBL:
 
         counts = np.zeros(g, dtype=np.uint64)
         self._chk(self._L.cbl_seq_contains_fused_dev(self._h, d_buf, offsets.ctypes.data_as(u64p), len(offsets) - 1, sp.ctypes.data_as(u32p), len(sp),
-                                                     arr(peer_region), arr(peer_ready), arr(peer_final), cap, d_pos, arr(recv_region), arr(answer_region),
-                                                     arr(ready), arr(final_counts), ticket, counts.ctypes.data_as(u64p)))
+                                                     arr(peer_region), arr(peer_final), cap, d_pos, arr(recv_region), arr(answer_region),
+                                                     arr(final_counts), epoch, counts.ctypes.data_as(u64p)))
         return counts
 
     def words_op_segments_dev(self, op: int, seg_ptrs, seg_n) -> None:

@@ -505,34 +505,33 @@ int32_t cbl_seq_route_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offset
     });
 }
 int32_t cbl_seq_contains_fused_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, const uint32_t* splitters,
-                                   uint32_t n_splitters, void* const* peer_region, void* const* peer_ready, void* const* peer_final, uint64_t cap,
-                                   uint32_t* d_pos, const void* const* recv_region, uint8_t* const* answer_region, const void* const* ready,
-                                   const void* const* final_counts, void* ticket, uint64_t* counts) {
+                                   uint32_t n_splitters, void* const* peer_region, void* const* peer_final, uint64_t cap, uint32_t* d_pos,
+                                   void* const* recv_region, uint8_t* const* answer_region, const void* const* final_counts, uint32_t epoch,
+                                   uint64_t* counts) {
     return guard(h, [&] {
-        need(h, "handle"); need(d_buf, "d_buf"); need(offsets, "offsets"); need(peer_region, "peer_region"); need(peer_ready, "peer_ready");
-        need(peer_final, "peer_final"); need(d_pos, "d_pos"); need(recv_region, "recv_region"); need(answer_region, "answer_region");
-        need(ready, "ready"); need(final_counts, "final_counts"); need(ticket, "ticket"); need(counts, "counts");
+        need(h, "handle"); need(d_buf, "d_buf"); need(offsets, "offsets"); need(peer_region, "peer_region"); need(peer_final, "peer_final");
+        need(d_pos, "d_pos"); need(recv_region, "recv_region"); need(answer_region, "answer_region"); need(final_counts, "final_counts");
+        need(counts, "counts");
         if (n_splitters) need(splitters, "splitters");
         FusedQuery q;
         q.splitters = splitters; q.n_split = n_splitters;
         q.peer_region = peer_region;
-        q.peer_ready = reinterpret_cast<unsigned* const*>(peer_ready);
         q.peer_final = reinterpret_cast<unsigned long long* const*>(peer_final);
         q.cap = cap; q.d_pos = d_pos;
         q.recv_region = recv_region; q.answer_region = answer_region;
-        q.ready = reinterpret_cast<const unsigned* const*>(ready);
         q.final_ = reinterpret_cast<const unsigned long long* const*>(final_counts);
-        q.ticket = reinterpret_cast<unsigned*>(ticket);
+        q.epoch = epoch;
         h->ix->seq_contains_fused_dev(d_buf, offsets[n_seqs], offsets, n_seqs, q, counts);
     });
 }
-int32_t cbl_peer_zero(cbl_t* h, void* d_ptr, size_t bytes) {
+int32_t cbl_peer_fill(cbl_t* h, void* d_ptr, int32_t byte, size_t bytes) {
     return guard(h, [&] {
         need(h, "handle");
         CUDA_CHECK(cudaSetDevice(h->ix->config().device));
-        if (d_ptr && bytes) { CUDA_CHECK(cudaMemsetAsync(d_ptr, 0, bytes, h->ix->stream())); CUDA_CHECK(cudaStreamSynchronize(h->ix->stream())); }
+        if (d_ptr && bytes) { CUDA_CHECK(cudaMemsetAsync(d_ptr, byte, bytes, h->ix->stream())); CUDA_CHECK(cudaStreamSynchronize(h->ix->stream())); }
     });
 }
+int32_t cbl_peer_zero(cbl_t* h, void* d_ptr, size_t bytes) { return cbl_peer_fill(h, d_ptr, 0, bytes); }
 // ---- peer memory: plain cudaMalloc blocks shared between the processes of one box with CUDA IPC ----
 int32_t cbl_peer_alloc(cbl_t* h, size_t bytes, void** d_ptr, uint8_t* handle) {
     return guard(h, [&] {

@@ -28,15 +28,13 @@ struct FusedQuery {
     const uint32_t* splitters;
     uint32_t n_split;
     void* const* peer_region;                    // [g] this rank's region inside owner d's receive buffer
-    unsigned* const* peer_ready;                 // [g] this rank's row of block counters at owner d
     unsigned long long* const* peer_final;       // [g] this rank's final-count slot at owner d
-    uint64_t cap;                                // words per region (multiple of 2048)
+    uint64_t cap;                                // words per region (multiple of 1024)
     uint32_t* d_pos;                             // [k-mers] answer slot of every local k-mer (d * cap + index inside region d)
-    const void* const* recv_region;              // [g] region of this rank's receive buffer written by source s
+    void* const* recv_region;                    // [g] region of this rank's receive buffer written by source s (sentinel-filled)
     uint8_t* const* answer_region;               // [g] this rank's region inside source s's answer buffer
-    const unsigned* const* ready;                // [g] local block counters of source s
     const unsigned long long* const* final_;     // [g] local final-count slot of source s
-    unsigned* ticket;                            // local, zero on entry
+    uint32_t epoch;                              // 1 .. 65535: same on every rank, different from the previous call's
 };
 
 class IIndex {

@@ -22,6 +22,7 @@
 #endif
 #include "sanitize.cuh"
 #include "seq_words.cuh"
+#include "shard_query.cuh"
 
 namespace cbl {
 
@@ -1224,72 +1225,65 @@ public:
         if (h[16] != ULLONG_MAX) throw_bad_byte(h[16]);
         for (uint32_t i = 0; i <= n_split; i++) counts[i] = h[i];
     }
-    // The fused sharded query of one rank (see ShardArgs in seq_words.cuh): the producer (encode + necklace + route, MODE 2
-    // with block signalling) runs on a side stream, the consumer (MODE 4: probes blocks of words as the peers complete
-    // them, answers stored straight into the asking rank's buffer) on the handle's stream, both with capped, persistent
-    // grids so that they are co-resident on every SM: the integer work of the producer hides under the memory stalls of
-    // the consumer the way the two halves of the single-GPU fused kernel do, and no host round trip separates routing
-    // from probing.  Returns when both kernels are done; counts[d] = words sent to owner d (> cap: overflow, retry).
+    // The fused sharded query of one rank (shard_query.cuh): ONE kernel whose warps alternate between producing (encode +
+    // necklace + route of this rank's reads, words stored straight into their owners' receive regions) and consuming
+    // (probing the blocks of words the peers have completed in this rank's receive buffer, answers stored straight into
+    // the asking rank's answer buffer).  Returns when the kernel is done, i.e. when this rank has answered every block sent
+    // to it; counts[d] = words sent to owner d (> cap: overflow, the caller retries with larger regions).
     void seq_contains_fused_dev(const uint8_t* d_seq, uint64_t n_bytes, const uint64_t* offsets, size_t n_seqs, const FusedQuery& q,
                                 uint64_t* counts) override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         check_records(offsets, n_seqs);
         const uint32_t g = q.n_split + 1;
-        if (g > ROUTE_MAX_SPLIT + 1 || g > PROBE_MAX_SEG) throw Error(CBL_EINVAL, "too many ranks");
+        if (g > (uint32_t)SQ_MAX_RANKS) throw Error(CBL_EINVAL, "too many ranks");
         if ((uint64_t)g * q.cap >= (1ull << 32)) throw Error(CBL_EINVAL, "fused query: (ranks x region capacity) must stay below 2^32 words");
-        if (q.cap % CHUNK_KMERS) throw Error(CBL_EINVAL, "fused query: region capacity must be a multiple of 2048 words");
+        if (q.cap % SQ_BLOCK) throw Error(CBL_EINVAL, "fused query: region capacity must be a multiple of " + std::to_string(SQ_BLOCK) + " words");
+        if (q.epoch == 0 || q.epoch > 65535) throw Error(CBL_EINVAL, "fused query: epoch must be in 1 .. 65535");
         for (uint32_t i = 0; i < g; i++) counts[i] = 0;
-        cudaStream_t ps = side_[0];
         ensure_sub();
-        int sms = 0;
-        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device));
-        // ---- producer
         PieceList pl;
         build_pieces(offsets, 0, n_seqs, pl);
+        if (2 * pl.n_chunks >= (1ull << 32)) throw Error(CBL_EINVAL, "fused query: too many chunks in one call");
         DevPieces dp;
-        DevBuf<unsigned long long> cnt(17, ps);   // [16] per-owner counters, [16] = error offset
-        CUDA_CHECK(cudaMemsetAsync(cnt.get(), 0, 16 * 8, ps));
-        CUDA_CHECK(cudaMemsetAsync(cnt.get() + 16, 0xFF, 8, ps));
-        if (!pl.kmers.empty()) {
-            upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, ps);
-            ShardArgs<W> sa{};
-            sa.dest = make_dest_digit(q.splitters, q.n_split);
-            for (uint32_t i = 0; i <= ROUTE_MAX_SPLIT; i++) {
-                sa.peer[i] = i < g ? (W*)q.peer_region[i] : nullptr;
-                sa.peer_ready[i] = i < g ? q.peer_ready[i] : nullptr;
-            }
-            sa.cnt = cnt.get();
-            sa.pos = q.d_pos;
-            sa.cap = q.cap;
-            const unsigned grid = (unsigned)std::min<uint64_t>(dp.batch.n_chunks, (uint64_t)sms * env_u64("CBL_FUSED_PROD", 6));
-            CBL_LAUNCH((seq_words_kernel<W, Suf, 2, false, 32, 1>), grid, SW_THREADS, 0, ps, dp.batch, P_, (W*)nullptr, (uint8_t*)nullptr, view(),
-                       cnt.get() + 16, sa);
+        if (!pl.kmers.empty()) upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, st_);
+        // [0, 16) words reserved per owner, [16] their sum, [17] smallest offending byte offset, [18] time-out flag, [19] task counter | block ticket (2 x u32)
+        DevBuf<unsigned long long> ctl(20, st_);
+        CUDA_CHECK(cudaMemsetAsync(ctl.get(), 0, 20 * 8, st_));
+        CUDA_CHECK(cudaMemsetAsync(ctl.get() + 17, 0xFF, 8, st_));
+        ShardQueryArgs<W> a{};
+        for (int i = 0; i < ROUTE_MAX_SPLIT; i++) a.split[i] = (uint32_t)i < q.n_split ? q.splitters[i] : 0xFFFFFFFFu;
+        a.suffix_bits = P_.suffix_bits;
+        for (uint32_t i = 0; i < (uint32_t)SQ_MAX_RANKS; i++) {
+            a.peer[i] = i < g ? (W*)q.peer_region[i] : nullptr;
+            a.peer_final[i] = i < g ? q.peer_final[i] : nullptr;
+            a.seg_words[i] = i < g ? (W*)q.recv_region[i] : nullptr;
+            a.seg_out[i] = i < g ? q.answer_region[i] : nullptr;
+            a.final_[i] = i < g ? q.final_[i] : nullptr;
         }
-        {
-            PeerFinals pf;
-            for (uint32_t i = 0; i <= ROUTE_MAX_SPLIT; i++) pf.p[i] = i < g ? q.peer_final[i] : nullptr;
-            CBL_LAUNCH(publish_finals_kernel, 1, 32, 0, ps, cnt.get(), (unsigned long long)q.cap, pf, (int)g);
-        }
-        CUDA_CHECK(cudaMemcpyAsync(h_status_, cnt.get(), 17 * 8, cudaMemcpyDeviceToHost, ps));
-        // ---- consumer
-        {
-            ShardArgs<W> sa{};
-            for (uint32_t i = 0; i < g; i++) {
-                sa.seg_words[i] = (const W*)q.recv_region[i];
-                sa.seg_out[i] = q.answer_region[i];
-                sa.ready[i] = q.ready[i];
-                sa.final_[i] = q.final_[i];
-            }
-            sa.n_seg = (int)g;
-            sa.ticket = q.ticket;
-            sa.max_blocks = (uint32_t)(q.cap / CHUNK_KMERS);
-            const unsigned grid = (unsigned)((uint64_t)sms * env_u64("CBL_FUSED_CONS", 10));
-            CBL_LAUNCH((seq_words_kernel<W, Suf, 4, false, CBL_PROBE_WB, 1>), grid, SW_THREADS, 0, st_, SeqBatch{}, P_, (W*)nullptr, (uint8_t*)nullptr,
-                       view(), (unsigned long long*)nullptr, sa);
-        }
-        CUDA_CHECK(cudaStreamSynchronize(ps));
+        a.cnt = ctl.get();
+        a.err = ctl.get() + 17;
+        a.prod_next = reinterpret_cast<unsigned*>(ctl.get() + 19);
+        a.ticket = a.prod_next + 1;
+        a.epoch = q.epoch;
+        a.n_kmers = pl.n_kmers;
+        a.pos = q.d_pos;
+        a.cap = q.cap;
+        a.n_tasks = (uint32_t)(2 * pl.n_chunks);
+        a.max_blocks = (uint32_t)(q.cap / SQ_BLOCK);
+        a.g = (int)g;
+        a.dev_flags = (int)env_u64("CBL_SQ_FLAGS", 0);
+        static int occ = 0;
+        if (!occ) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shard_query_kernel<W, Suf, CBL_PROBE_WB>, SQ_THREADS, 0));
+        int sms = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device));
+        // persistent grid: every resident warp keeps taking produce tasks and block tickets until both run out
+        const unsigned grid = (unsigned)((uint64_t)sms * std::min<uint64_t>(env_u64("CBL_SQ_CTAS", (uint64_t)std::max(occ, 1)), 32));
+        SeqBatch sb = pl.kmers.empty() ? SeqBatch{} : dp.batch;
+        CBL_LAUNCH((shard_query_kernel<W, Suf, CBL_PROBE_WB>), grid, SQ_THREADS, 0, st_, sb, P_, view(), a);
+        CUDA_CHECK(cudaMemcpyAsync(h_status_, ctl.get(), 19 * 8, cudaMemcpyDeviceToHost, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
-        if (h_status_[16] != ULLONG_MAX) throw_bad_byte(h_status_[16]);
+        if (h_status_[18] != 0) throw Error(CBL_ECUDA, "fused query: timed out waiting for the words of another rank (is every rank of the group in the call?)");
+        if (h_status_[17] != ULLONG_MAX) throw_bad_byte(h_status_[17]);
         for (uint32_t i = 0; i < g; i++) counts[i] = h_status_[i];
     }
     void gather_u8_dev(const uint8_t* d_src, const uint32_t* d_pos, uint64_t n, uint8_t* d_out) override {

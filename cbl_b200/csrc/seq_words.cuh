@@ -39,16 +39,6 @@ template <class W> struct ShardArgs {
     // counts digit hist_first + p, p < hist_np <= SW_HIST_MAX; null = no histogram
     unsigned long long* hist = nullptr;
     int hist_first = 0, hist_np = 0;
-    // MODE 2 + MODE 4 = the fused sharded query (producer / consumer over NVLink peer memory, no host round trip between
-    // routing and probing): a region is cut into blocks of CHUNK_KMERS words; the producer that stored c words of a
-    // (chunk, owner) run adds c to the owner's counter of the block(s) they fell into (system-scope release after the
-    // stores), so block b of source s is complete when ready[s][b] == CHUNK_KMERS, or, for the last block, when it
-    // equals what is left of final[s] - 1 words (final: 0 = not yet published, STREAM_OVERFLOW = region overflowed).
-    unsigned* peer_ready[ROUTE_MAX_SPLIT + 1];     // MODE 2: this rank's row of block counters at owner d (null: no signalling)
-    const unsigned* ready[PROBE_MAX_SEG];          // MODE 4: block counters of source s (local memory, written by the peers)
-    const unsigned long long* final_[PROBE_MAX_SEG];   // MODE 4: final word count of source s + 1
-    unsigned* ticket = nullptr;                    // MODE 4: next (block, source) pair to probe (zeroed by the caller)
-    uint32_t max_blocks = 0;                       // MODE 4: blocks per region (capacity / CHUNK_KMERS)
     DestDigit<W> dest;                    // MODE 2: owner rank of a word
     W* peer[ROUTE_MAX_SPLIT + 1];         // MODE 2
     unsigned long long* cnt = nullptr;    // MODE 2: [16] words reserved per owner (zeroed by the caller)
@@ -135,7 +125,7 @@ template <> __device__ __forceinline__ u128 cut_window<u128>(uint64_t A, uint64_
 
 // MODE 0: write words (W) to out_words.   MODE 1: probe the index, write one byte per k-mer.
 // MODE 2: fused route (sharded path, source side): the words go straight to their owner ranks, see ShardArgs.
-// MODE 3: the words are read from sa.in_words instead of being computed (sharded path, owner side, and the
+// MODE 3: the words are read from sa.seg_words instead of being computed (sharded path, owner side, and the
 //         word-level contains of the C ABI); answers to out_flags.
 // BRUTE: use the normative brute-force necklace instead of the fast one (debug / cross-check).
 // U: k-mers per lane processed together.  In MODE 1 the U lookups advance in lock step (directory
@@ -149,12 +139,12 @@ template <> __device__ __forceinline__ u128 cut_window<u128>(uint64_t A, uint64_
 #define CBL_SW_MIN_BLOCKS 24   // fused probe: latency bound, occupancy beats a few spilled registers (measured)
 #endif
 template <class W, class Suf, int MODE, bool BRUTE, int WB, int U>
-__global__ void __launch_bounds__(SW_THREADS, ((MODE == 3 || MODE == 4) && U == 1) ? CBL_SW_MIN_BLOCKS_WORDS : ((MODE == 1 && U == 1) ? CBL_SW_MIN_BLOCKS : 1)) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
+__global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN_BLOCKS_WORDS : ((MODE == 1 && U == 1) ? CBL_SW_MIN_BLOCKS : 1)) seq_words_kernel(SeqBatch b, KParams P, W* __restrict__ out_words,
                                                                uint8_t* __restrict__ out_flags, IndexView<Suf> ix,
                                                                unsigned long long* __restrict__ err_pos, ShardArgs<W> sa) {
     static_assert(32 % U == 0, "U must divide 32");
     constexpr int WN = Window<Suf, WB>::N;
-    constexpr bool WORDS_IN = MODE == 3 || MODE == 4;   // the words are read, not computed
+    constexpr bool WORDS_IN = MODE == 3;   // the words are read, not computed
     constexpr bool PROBE = MODE == 1 || WORDS_IN;
     constexpr int QN = PROBE ? PENDING_CAP : 1;
     // MODE 2: the chunk's words (by output slot), owner | rank-inside-owner of every slot, slots in owner order
@@ -234,51 +224,14 @@ __global__ void __launch_bounds__(SW_THREADS, ((MODE == 3 || MODE == 4) && U == 
         q_push(und, s, L, R, g, a.w, slot_it);
     };
     const uint64_t n_chunks = MODE == 3 ? sa.seg_chunk0[sa.n_seg] : b.n_chunks;
-    __shared__ uint32_t s_ticket[2];   // MODE 4: {ticket, words of the block (0: skip, 0xFFFFFFFF: no tickets left)}
-    for (uint64_t chunk = blockIdx.x; MODE == 4 || chunk < n_chunks; chunk += gridDim.x) {
+    for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         int m;
         W* ow = nullptr;
         uint8_t* of = nullptr;
         uint32_t* opos = nullptr;
         uint64_t Wd = 0, H = 0;
         const W* in_words = nullptr;   // MODE 3 / 4: first word of this chunk
-        if (MODE == 4) {
-            // take the next (block, source) pair and wait until its words have landed (or it is known not to exist)
-            if (threadIdx.x == 0) {
-                const uint32_t t = atomicAdd(sa.ticket, 1u);
-                const uint32_t src = t % (uint32_t)sa.n_seg, blk = t / (uint32_t)sa.n_seg;
-                uint32_t mm = 0xFFFFFFFFu;
-                if (blk < sa.max_blocks) {
-                    const unsigned* rp = sa.ready[src] + blk;
-                    for (;;) {
-                        unsigned r;
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(r) : "l"(rp) : "memory");
-                        if (r == (unsigned)CHUNK_KMERS) { mm = CHUNK_KMERS; break; }
-                        unsigned long long f;
-                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(sa.final_[src]) : "memory");
-                        if (f != 0) {
-                            if (f == STREAM_OVERFLOW) { mm = 0; break; }
-                            const unsigned long long total = f - 1, first = (unsigned long long)blk * CHUNK_KMERS;
-                            const unsigned long long rem = total > first ? min((unsigned long long)CHUNK_KMERS, total - first) : 0ull;
-                            if (rem == 0) { mm = 0; break; }
-                            if (r == rem) { mm = (uint32_t)rem; break; }
-                        }
-                        __nanosleep(200);
-                    }
-                }
-                s_ticket[0] = t;
-                s_ticket[1] = mm;
-            }
-            __syncthreads();
-            const uint32_t t = s_ticket[0], mm = s_ticket[1];
-            __syncthreads();
-            if (mm == 0xFFFFFFFFu) break;     // block-uniform
-            if (mm == 0) continue;
-            const uint32_t src = t % (uint32_t)sa.n_seg, blk = t / (uint32_t)sa.n_seg;
-            m = (int)mm;
-            of = sa.seg_out[src] + (uint64_t)blk * CHUNK_KMERS;
-            in_words = sa.seg_words[src] + (uint64_t)blk * CHUNK_KMERS;
-        } else if (MODE == 3) {
+        if (MODE == 3) {
             int sg = 0;
 #pragma unroll
             for (int t = 1; t < PROBE_MAX_SEG; t++) sg += (t < sa.n_seg && sa.seg_chunk0[t] <= chunk) ? 1 : 0;
@@ -353,8 +306,7 @@ __global__ void __launch_bounds__(SW_THREADS, ((MODE == 3 || MODE == 4) && U == 
                 W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
                 slot[u] = (uint32_t)kidx;
                 if (WORDS_IN) {
-                    // MODE 4: the words were stored by a peer GPU moments ago: read them past L1 (ld.cg)
-                    word[u] = active[u] ? (MODE == 4 ? ld_cg_word(in_words + kidx) : in_words[kidx]) : (W)0;
+                    word[u] = active[u] ? in_words[kidx] : (W)0;
                     continue;
                 }
                 if (P.canonical) {
@@ -497,19 +449,6 @@ __global__ void __launch_bounds__(SW_THREADS, ((MODE == 3 || MODE == 4) && U == 
                 const uint32_t bd = s_base[d];
                 if (bd != 0xFFFFFFFFu) s_peer[d][(size_t)bd + ((uint32_t)q - s_off[d])] = s_stage[s_inv[q]];
             }
-            if (sa.peer_ready[0] != nullptr) {   // fused query: tell every owner which blocks of my region grew
-                __syncthreads();                 // the CTA's stores are issued
-                if (threadIdx.x < 16) {
-                    const uint32_t c = s_off[threadIdx.x + 1] - s_off[threadIdx.x], bd = s_base[threadIdx.x];
-                    if (c && bd != 0xFFFFFFFFu) {
-                        __threadfence_system();  // ... and ordered before the counters move (release, system scope)
-                        const uint32_t b0 = bd / CHUNK_KMERS, n0 = min(c, (b0 + 1) * CHUNK_KMERS - bd);
-                        unsigned* rp = sa.peer_ready[threadIdx.x] + b0;
-                        asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(rp), "r"(n0) : "memory");
-                        if (c > n0) asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(rp + 1), "r"(c - n0) : "memory");
-                    }
-                }
-            }
         }
         if (do_hist) {   // the chunk's counters: lane run counters -> shared, then one global RED per digit value that occurred
             if (hc_n0) atomicAdd(&s_hist[(sa.hist_np - 2) * 256 + hc_d0], hc_n0);
@@ -521,21 +460,6 @@ __global__ void __launch_bounds__(SW_THREADS, ((MODE == 3 || MODE == 4) && U == 
         }
         __syncthreads();  // s_piece / s_fwd / s_flags / s_hist reuse in the next grid-stride iteration
     }
-}
-
-// fused sharded query: after the producer kernel (MODE 2) of a rank has finished, publish how many words it sent to
-// every owner (count + 1; STREAM_OVERFLOW when the region ran out of capacity), so the owners' consumers can finish the
-// last, partly filled block of the region and stop
-struct PeerFinals {
-    unsigned long long* p[ROUTE_MAX_SPLIT + 1];
-};
-static __global__ void publish_finals_kernel(const unsigned long long* __restrict__ cnt, unsigned long long cap, PeerFinals pf, int n_owner) {
-    const int d = threadIdx.x;
-    if (d >= n_owner || pf.p[d] == nullptr) return;
-    const unsigned long long c = cnt[d];
-    const unsigned long long v = c > cap ? STREAM_OVERFLOW : c + 1;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(pf.p[d]), "l"(v) : "memory");
 }
 
 // k-mer integers (lo/hi arrays) -> words; single-k-mer API (src/cbl.rs:199-235)

@@ -214,7 +214,9 @@ class PeerExchange:
         self.own_recv = self.own_back = self.own_ctrl = 0
         self.peer_recv: List[int] = []
         self.peer_back: List[int] = []
-        self.peer_ctrl: List[int] = []   # control blocks of the fused query: block counters, final counts, ticket
+        self.peer_ctrl: List[int] = []   # control blocks of the fused query: one final-count slot per source rank
+        self.recv_dirty = True           # the receive buffer may hold something else than 0xFF (see clean_recv)
+        self.epoch = 0                   # call counter of the fused query (same on every rank: the calls are collective)
 
     def barrier(self):
         if self.ctrl.type == "cpu":
@@ -263,27 +265,29 @@ class PeerExchange:
         self.peer_back = [self.own_back if r == self.rank else self.cbl.peer_open(handles[r][1]) for r in range(self.world)]
         self.peer_ctrl = [self.own_ctrl if r == self.rank else self.cbl.peer_open(handles[r][2]) for r in range(self.world)]
         self.cbl.peer_zero(self.own_ctrl, self.ctrl_bytes())
+        self.recv_dirty = True
         self.barrier()
 
-    # control block of the fused query (one per rank, peer-mapped): [world rows of cap/2048 u32 block counters]
-    # [world u64 final counts][u32 ticket]; row / slot s belongs to source rank s
-    def blocks(self) -> int:
-        return self.cap // 2048
-
+    # control block of the fused query (one per rank, peer-mapped): one u64 final-count slot per source rank, tagged with
+    # the call's epoch by the source (csrc/shard_query.cuh), so it is zeroed once and never again
     def ctrl_bytes(self) -> int:
-        return self.world * self.blocks() * 4 + self.world * 8 + 64
-
-    def ready_row(self, base: int, src: int) -> int:
-        return base + src * self.blocks() * 4
+        return self.world * 8 + 64
 
     def final_slot(self, base: int, src: int) -> int:
-        return base + self.world * self.blocks() * 4 + src * 8
+        return base + src * 8
 
-    def ticket(self) -> int:
-        return self.own_ctrl + self.world * self.blocks() * 4 + self.world * 8
+    def clean_recv(self):
+        """Collective.  The fused query wants 0xFF in every slot of the receive buffers that holds no word (a word is its own
+        arrival flag); it leaves them that way itself, so this runs after allocation, after the buffers served another path
+        (mutations, the two-kernel query) and after an overflowed or failed call."""
+        if self.recv_dirty:
+            self.cbl.peer_fill(self.own_recv, 0xFF, self.SLOTS * self.world * self.cap * self.word_bytes)
+            self.recv_dirty = False
+            self.barrier()   # nobody stores into a buffer that is still being filled
 
-    def zero_ctrl(self):
-        self.cbl.peer_zero(self.own_ctrl, self.ctrl_bytes())
+    def next_epoch(self) -> int:
+        self.epoch = self.epoch % 65535 + 1
+        return self.epoch
 
     def my_regions(self, slot: int = 0) -> List[int]:
         """my region inside every owner's receive buffer (buffer set ``slot``)"""
@@ -390,6 +394,7 @@ class ShardedCBL:
         torch.cuda.current_stream(self.device).synchronize()
         while True:
             px.ensure(cap)
+            px.recv_dirty = True
             counts = cbl.seq_route_dev(d_buf, offsets, self.splitters_u32, px.my_regions(), px.cap, pos.data_ptr() if want_pos else 0)
             C = px.all_counts(counts)                                # barrier: all words have landed
             if int(C.max()) <= px.cap:
@@ -461,43 +466,48 @@ class ShardedCBL:
     # for the same SM resources when co-resident (each slows down by what the other takes), so the default is 1.
     PIPE = 1
 
-    # CBL_FUSED=1 selects the producer + consumer kernels with block signalling; measured on 2 x B200 (bench.py, 1 Gbp per
-    # rank): 46.0 ms per step against 39.9 ms for route kernel -> count exchange -> one probe launch: co-resident, the two
-    # kernels are both bound by instruction issue and the capped grids cost occupancy
-    FUSED = 0
+    # The default query path is the fused kernel (csrc/shard_query.cuh): measured on 8 x B200 / 2 x B200 (bench.py, 1 Gbp per
+    # rank) against route kernel -> count exchange -> one probe launch (CBL_FUSED=0), see DESIGN.md section 7.
+    FUSED = 1
 
     def _peer_contains_fused(self, d_buf: int, offsets: np.ndarray) -> torch.Tensor:
-        """contains_seq of this rank's reads as ONE producer + ONE consumer kernel per rank (cbl_seq_contains_fused_dev): words
-        travel to their owners and answers back over NVLink peer memory while both kernels run; the process group only
-        carries two small count exchanges per call (region sizing / "everything has landed")."""
+        """contains_seq of this rank's reads as ONE kernel per rank (cbl_seq_contains_fused_dev, csrc/shard_query.cuh): every
+        warp alternates between producing (encode + necklace + route of this rank's reads) and probing the blocks of words
+        the peers have completed in this rank's buffer; words travel to their owners and answers back over NVLink peer
+        memory while the kernel runs.  The process group carries ONE count exchange per call (region overflow check and
+        "every answer has landed")."""
         px, cbl = self.peer, self.engine.cbl
         n = cbl.count_kmers(offsets)
-        # doubles as the barrier "every rank is done with the buffers of the previous call"
-        n_max = int(px.all_counts(np.array([n], dtype=np.uint64)).max())
-        cap = int(n_max / self.world * float(os.environ.get("CBL_ROUTE_SLACK", self.SLACK))) + 4096
+        # Region sizing needs an exchange on the first call only (see _peer_contains); the previous call ended with "all
+        # answers have landed", so nobody is still using the buffers
+        if px.cap == 0:
+            n_max = int(px.all_counts(np.array([n], dtype=np.uint64)).max())
+            cap = int(n_max / self.world * float(os.environ.get("CBL_ROUTE_SLACK", self.SLACK))) + 4096
+        else:
+            cap = px.cap
         pos = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
         out = torch.empty(n, dtype=torch.uint8, device=self.device)
         torch.cuda.current_stream(self.device).synchronize()
-        g, me = self.world, self.rank
+        g = self.world
         while True:
             px.ensure(cap)
-            px.zero_ctrl()
-            px.barrier()                                             # every rank's counters are zero before anybody produces
+            px.clean_recv()
+            epoch = px.next_epoch()
+            px.recv_dirty = True           # until the call has come back clean
             counts = cbl.seq_contains_fused_dev(
                 d_buf, offsets, self.splitters_u32,
                 peer_region=px.my_regions(),
-                peer_ready=[px.ready_row(px.peer_ctrl[d], me) for d in range(g)],
-                peer_final=[px.final_slot(px.peer_ctrl[d], me) for d in range(g)],
+                peer_final=[px.final_slot(px.peer_ctrl[d], self.rank) for d in range(g)],
                 cap=px.cap, d_pos=pos.data_ptr(),
                 recv_region=[px.recv_region(s_) for s_ in range(g)],
                 answer_region=[px.answer_region(s_) for s_ in range(g)],
-                ready=[px.ready_row(px.own_ctrl, s_) for s_ in range(g)],
                 final_counts=[px.final_slot(px.own_ctrl, s_) for s_ in range(g)],
-                ticket=px.ticket())
+                epoch=epoch)
             C = px.all_counts(counts)                                # barrier: every consumer is done => my answers have landed
             if int(C.max()) <= px.cap:
+                px.recv_dirty = False                                # every word that arrived was consumed and its slot reset
                 break
-            cap = int(int(C.max()) * 1.1) + 4096                     # a region overflowed somewhere: everybody retries
+            cap = int(int(C.max()) * 1.1) + 4096                     # a region overflowed somewhere: everybody refills and retries
         if n:
             cbl.gather_u8_dev(px.answers(), pos.data_ptr(), n, out.data_ptr())
         return out
@@ -560,6 +570,7 @@ class ShardedCBL:
 
         while True:
             px.ensure(cap)
+            px.recv_dirty = True
             worker, prev, overflow = None, None, 0
             for b in range(pipe):
                 slot = b & 1

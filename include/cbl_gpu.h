@@ -168,22 +168,29 @@ int32_t cbl_route_scatter_dev(cbl_t* h, const void* d_words, size_t n, const uin
  * d_out = that peer pointer).  (n_splitters+1) * cap < 2^32.  Returns when the stores are complete. */
 int32_t cbl_seq_route_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, const uint32_t* splitters,
                           uint32_t n_splitters, void* const* peer_region, uint64_t cap, uint32_t* d_pos, uint64_t* counts);
-/* The fused sharded contains_seq of one rank: ONE producer kernel (2-bit encode + necklace + route, every word stored
- * straight into its owner's receive buffer over NVLink) and ONE consumer kernel (membership probe of the words the peers
- * stored here, every answer stored straight back into the asking rank's answer buffer) run side by side on every SM; the
- * producer tells the owners which 2048-word blocks of its regions are complete through counters in peer memory, so no
- * host round trip or collective separates routing from probing (src/cbl.rs:311-324 for a prefix-sharded set).
- * Arrays of g = n_splitters + 1 pointers, indexed by rank: peer_region / peer_ready / peer_final = THIS rank's region
- * (cap words, cap a multiple of 2048), row of cap / 2048 u32 block counters and u64 final-count slot at owner d;
- * recv_region / ready / final_counts = the same objects of source s in THIS rank's own buffers; answer_region = this
- * rank's region (cap bytes) in source s's answer buffer; ticket = a zeroed u32.  All counters must be zero on every
- * rank before any rank calls (zero with cbl_peer_zero, then a barrier).  d_pos and counts as for cbl_seq_route_dev.
- * Returns when both kernels of THIS rank are done; a barrier over all ranks then guarantees every answer has landed. */
+/* The fused sharded contains_seq of one rank (src/cbl.rs:311-324 for a prefix-sharded set) as ONE kernel per GPU
+ * (cbl_b200/csrc/shard_query.cuh): every warp alternates between producing (2-bit encode + necklace + route of this
+ * rank's reads, every word stored straight into its owner's receive buffer over NVLink) and consuming (membership probe
+ * of the 1024-word blocks the peers have completed in THIS rank's receive buffer, every answer stored straight back into
+ * the asking rank's answer buffer), so the integer work of the necklace hides under the memory stalls of the probe as it
+ * does in the single-GPU kernel and no host round trip or collective separates routing from probing.
+ * The receive buffers must hold 0xFF bytes wherever no word has been stored (cbl_peer_fill once after allocation and
+ * after any other use of the buffer, e.g. cbl_seq_route_dev, or a failed / overflowed call): an all-ones word is never
+ * valid, so a word is its own arrival flag, and the consumer puts the 0xFF back as it reads.
+ * Arrays of g = n_splitters + 1 pointers, indexed by rank: peer_region / peer_final = THIS rank's region (cap words, cap
+ * a multiple of 1024) and u64 final-count slot at owner d; recv_region / final_counts = the same objects of source s in
+ * THIS rank's own buffers; answer_region = this rank's region (cap bytes) in source s's answer buffer.  epoch: 1..65535,
+ * the same on every rank and different from the previous call's (the final-count slots carry it, so they need no
+ * zeroing).  Every rank of the group must make the call (a rank without reads passes n_seqs = 0); a rank whose peers
+ * never show up fails with CBL_ECUDA after 20 s.  d_pos and counts as for cbl_seq_route_dev (counts[d] > cap:
+ * overflow, refill the buffers and retry with a larger cap).  Returns when the kernel of THIS rank is done, i.e. when it
+ * has answered every block sent to it; a barrier over all ranks then guarantees every answer has landed. */
 int32_t cbl_seq_contains_fused_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, const uint32_t* splitters,
-                                   uint32_t n_splitters, void* const* peer_region, void* const* peer_ready, void* const* peer_final, uint64_t cap,
-                                   uint32_t* d_pos, const void* const* recv_region, uint8_t* const* answer_region, const void* const* ready,
-                                   const void* const* final_counts, void* ticket, uint64_t* counts);
-int32_t cbl_peer_zero(cbl_t* h, void* d_ptr, size_t bytes);           /* zero a block of (own) device memory, synchronous */
+                                   uint32_t n_splitters, void* const* peer_region, void* const* peer_final, uint64_t cap, uint32_t* d_pos,
+                                   void* const* recv_region, uint8_t* const* answer_region, const void* const* final_counts, uint32_t epoch,
+                                   uint64_t* counts);
+int32_t cbl_peer_fill(cbl_t* h, void* d_ptr, int32_t byte, size_t bytes);   /* memset a block of (own) device memory, synchronous */
+int32_t cbl_peer_zero(cbl_t* h, void* d_ptr, size_t bytes);           /* = cbl_peer_fill(.., 0, ..) */
 int32_t cbl_word_bytes(const cbl_t* h, int32_t* out);      /* 8 or 16: size of one device word */
 int32_t cbl_suffix_bits(const cbl_t* h, int32_t* out);
 

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench, cbl_b200
 dev = torch.device("cuda", 0)
-K, rec = bench.K, 1_000_000
+K, rec = 25, 1_000_000
 index, i_off, query, q_off = bench.make_workload(torch, dev, int(500e6), int(1000e6), rec, seed_base=0)
 n_q = (len(q_off) - 1) * (rec - K + 1)
 cbl = cbl_b200.CBL(K, 64, 24, canonical=False, device=0)

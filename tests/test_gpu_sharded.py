@@ -1,7 +1,7 @@
 """The sharded GPU path end to end on ONE device: two processes share cuda:0, the control plane (count
 matrix, IPC handles, barriers) runs over gloo and the data path is the fused route + peer-memory exchange
 (CUDA IPC mappings of the other process's buffers; the query runs as route kernel -> count exchange -> one probe launch,
-or, "fused" modes, as producer + consumer kernels with block signalling through peer memory), checked bit-exactly
+or, "fused" modes, as the one-kernel fused query of csrc/shard_query.cuh), checked bit-exactly
 against the oracle.  The same code
 runs one process per GPU over NVLink on a multi-GPU box (bench.py --gpus N)."""
 import os
@@ -28,8 +28,8 @@ WORKER = textwrap.dedent(
         os.environ["CBL_ROUTE_SLACK"] = "0.7"
     if "pipe" in MODE:    # pipelined query: 3 sub-batches, route of b + 1 overlapping the probe of b, two buffer sets
         os.environ["CBL_PIPE"] = "3"
-    # default query path: route kernel, count exchange, ONE probe launch; "fused": producer + consumer kernels with block
-    # signalling through peer memory (cbl_seq_contains_fused_dev)
+    # "fused" (the default of ShardedCBL): one kernel per rank whose warps alternate between routing and probing
+    # (cbl_seq_contains_fused_dev); otherwise: route kernel, count exchange, ONE probe launch
     os.environ["CBL_FUSED"] = "1" if "fused" in MODE else "0"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
