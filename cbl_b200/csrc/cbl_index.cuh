@@ -35,6 +35,7 @@ struct FusedQuery {
     uint8_t* const* answer_region;               // [g] this rank's region inside source s's answer buffer
     const unsigned long long* const* final_;     // [g] local final-count slot of source s
     uint32_t epoch;                              // 1 .. 65535: same on every rank, different from the previous call's
+    uint32_t grid_share = 1;                     // ranks whose kernels share THIS device (they must all be resident together)
 };
 
 class IIndex {

@@ -1246,9 +1246,9 @@ public:
         if (2 * pl.n_chunks >= (1ull << 32)) throw Error(CBL_EINVAL, "fused query: too many chunks in one call");
         DevPieces dp;
         if (!pl.kmers.empty()) upload_pieces(pl, 0, pl.kmers.size(), 0, d_seq, n_bytes, dp, st_);
-        // [0, 16) words reserved per owner, [16] their sum, [17] smallest offending byte offset, [18] time-out flag, [19] task counter | block ticket (2 x u32)
-        DevBuf<unsigned long long> ctl(20, st_);
-        CUDA_CHECK(cudaMemsetAsync(ctl.get(), 0, 20 * 8, st_));
+        // [0, 16) words reserved per owner, [16] their sum, [17] smallest offending byte offset, [18] time-out flag, [19] / [20] globaltimer at kernel start / end of the production, [21] task counter | block ticket (2 x u32)
+        DevBuf<unsigned long long> ctl(22, st_);
+        CUDA_CHECK(cudaMemsetAsync(ctl.get(), 0, 22 * 8, st_));
         CUDA_CHECK(cudaMemsetAsync(ctl.get() + 17, 0xFF, 8, st_));
         ShardQueryArgs<W> a{};
         for (int i = 0; i < ROUTE_MAX_SPLIT; i++) a.split[i] = (uint32_t)i < q.n_split ? q.splitters[i] : 0xFFFFFFFFu;
@@ -1262,7 +1262,7 @@ public:
         }
         a.cnt = ctl.get();
         a.err = ctl.get() + 17;
-        a.prod_next = reinterpret_cast<unsigned*>(ctl.get() + 19);
+        a.prod_next = reinterpret_cast<unsigned*>(ctl.get() + 21);
         a.ticket = a.prod_next + 1;
         a.epoch = q.epoch;
         a.n_kmers = pl.n_kmers;
@@ -1273,15 +1273,26 @@ public:
         a.g = (int)g;
         a.dev_flags = (int)env_u64("CBL_SQ_FLAGS", 0);
         static int occ = 0;
-        if (!occ) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shard_query_kernel<W, Suf, CBL_PROBE_WB>, SQ_THREADS, 0));
+        if (!occ) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shard_query_kernel<W, Suf, CBL_PROBE_WB, false>, SQ_THREADS, 0));
         int sms = 0;
         CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device));
         // persistent grid: every resident warp keeps taking produce tasks and block tickets until both run out
-        const unsigned grid = (unsigned)((uint64_t)sms * std::min<uint64_t>(env_u64("CBL_SQ_CTAS", (uint64_t)std::max(occ, 1)), 32));
+        // (ranks that share a device split its CTA slots: the kernels wait for each other's words, so all must be resident)
+        const uint64_t per_sm = std::min<uint64_t>(env_u64("CBL_SQ_CTAS", (uint64_t)std::max(occ, 1)), 32);
+        const unsigned grid = (unsigned)std::max<uint64_t>((uint64_t)sms * per_sm / std::max<uint32_t>(q.grid_share, 1), 1);
         SeqBatch sb = pl.kmers.empty() ? SeqBatch{} : dp.batch;
-        CBL_LAUNCH((shard_query_kernel<W, Suf, CBL_PROBE_WB>), grid, SQ_THREADS, 0, st_, sb, P_, view(), a);
-        CUDA_CHECK(cudaMemcpyAsync(h_status_, ctl.get(), 19 * 8, cudaMemcpyDeviceToHost, st_));
+        if (P_.canonical) CBL_LAUNCH((shard_query_kernel<W, Suf, CBL_PROBE_WB, true>), grid, SQ_THREADS, 0, st_, sb, P_, view(), a);
+        else CBL_LAUNCH((shard_query_kernel<W, Suf, CBL_PROBE_WB, false>), grid, SQ_THREADS, 0, st_, sb, P_, view(), a);
+        const auto t_host = std::chrono::steady_clock::now();
+        CUDA_CHECK(cudaMemcpyAsync(h_status_, ctl.get(), 21 * 8, cudaMemcpyDeviceToHost, st_));
         CUDA_CHECK(cudaStreamSynchronize(st_));
+        if (getenv("CBL_SHARD_TRACE") != nullptr) {
+            unsigned long long sent = 0;
+            for (uint32_t i = 0; i < g; i++) sent += h_status_[i];
+            fprintf(stderr, "[fused query] device %d: production of %llu words complete %.2f ms after the kernel started; launch -> done %.2f ms (host)\n",
+                    cfg_.device, sent, (double)(h_status_[20] - h_status_[19]) * 1e-6,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host).count());
+        }
         if (h_status_[18] != 0) throw Error(CBL_ECUDA, "fused query: timed out waiting for the words of another rank (is every rank of the group in the call?)");
         if (h_status_[17] != ULLONG_MAX) throw_bad_byte(h_status_[17]);
         for (uint32_t i = 0; i < g; i++) counts[i] = h_status_[i];

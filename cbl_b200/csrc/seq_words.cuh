@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN
                     uint32_t prefix;
                     split_key<W, Suf>(word[u], P, prefix, s[u]);
                     k32[u] = key32<Suf>(s[u], P.suffix_bits);
-                    present[u] = active[u] && ix.nb != 0;
+                    present[u] = active[u] && ix.nb != 0 && (!WORDS_IN || (prefix >> P.prefix_bits) == 0);   // words handed in from outside may be anything
                     lo[u] = prefix;
                     de[u] = ldg_keep(ix.dir + (present[u] ? (prefix >> 5) : 0u));
                 }

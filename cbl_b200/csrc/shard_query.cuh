@@ -64,7 +64,8 @@ template <class W> struct ShardQueryArgs {
     unsigned* ticket;                                 // local, zero on entry
     uint32_t max_blocks;                              // cap / SQ_BLOCK
     int g;                                            // ranks
-    unsigned long long* err;                          // [0] smallest offending byte offset (ULLONG_MAX: none), [1] time-out flag
+    unsigned long long* err;                          // [0] smallest offending byte offset (ULLONG_MAX: none), [1] time-out flag,
+                                                      // [2] / [3] globaltimer at kernel start / when the production was complete (trace)
     int dev_flags;                                    // developer knobs (CBL_SQ_FLAGS): 1 = produce only (no answers), 2 = consume only after the production
 };
 
@@ -95,6 +96,7 @@ template <class W> __device__ __forceinline__ void publish_finals_dev(const Shar
         const unsigned long long v = (a.epoch << 48) | (c > a.cap ? SQ_FINAL_OVERFLOW : c + 1);
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.peer_final[lane]), "l"(v) : "memory");
     }
+    if (lane == 0) a.err[3] = sq_now_ns();
 }
 
 // everything a warp keeps in shared memory, in one block so that one base register addresses all of it.  A warp is
@@ -119,7 +121,8 @@ template <class W, class Suf> struct SqWarpMem {
     uint32_t cnt[16];
 };
 
-template <class W, class Suf, int WB>
+// CANON: the set is canonical (compile-time, so that the plain instantiation carries none of the F6 bookkeeping in registers)
+template <class W, class Suf, int WB, bool CANON>
 __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_kernel(SeqBatch b, KParams P, IndexView<Suf> ix, ShardQueryArgs<W> a) {
     constexpr int WN = Window<Suf, WB>::N;
     constexpr int QN = PENDING_CAP;
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
         s_w[0].cnt[threadIdx.x] = 0;
         s_w[1].cnt[threadIdx.x] = 0;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.err[2] = sq_now_ns();
     __syncthreads();   // the only block-level barrier: from here on the two warps are independent
     SqWarpMem<W, Suf>& wm = s_w[threadIdx.x >> 5];
 
@@ -162,11 +166,11 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
             if (bad) atomicMin(a.err, (unsigned long long)(b.piece_byte[piece] + ks + off));
         }
         const uint64_t Wd1 = __shfl_sync(0xffffffffu, lane == 0 ? H : Wd, (lane + 1) & 31);
-        const uint64_t Wd2 = __shfl_sync(0xffffffffu, lane < 2 ? H : Wd, (lane + 2) & 31);
+        const uint64_t Wd2 = sizeof(W) == 16 ? __shfl_sync(0xffffffffu, lane < 2 ? H : Wd, (lane + 2) & 31) : 0ull;   // a 64-bit window spans two packed words
         // canonical mode: answers of a chunk come "forward k-mers first, then the reverse-complemented ones";
         // lane j keeps the parity ballot of round j of this half, the other half contributes its forward count only
         uint32_t my_bal = 0, fwd_before = 0, nfwd_total = 0;
-        if (P.canonical) {
+        if (CANON) {
             for (int j = 0; j < 32; j++) {
                 const uint64_t A = __shfl_sync(0xffffffffu, Wd, j), B = __shfl_sync(0xffffffffu, Wd1, j), C = __shfl_sync(0xffffffffu, Wd2, j);
                 const W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
@@ -204,7 +208,8 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
 #pragma unroll 1
             for (int jj = 0; jj < SQ_UNIT / 32; jj++) {
                 const int j = j0 + jj;
-                const uint64_t A = __shfl_sync(0xffffffffu, Wd, j), B = __shfl_sync(0xffffffffu, Wd1, j), C = __shfl_sync(0xffffffffu, Wd2, j);
+                const uint64_t A = __shfl_sync(0xffffffffu, Wd, j), B = __shfl_sync(0xffffffffu, Wd1, j);
+                const uint64_t C = sizeof(W) == 16 ? __shfl_sync(0xffffffffu, Wd2, j) : 0ull;
                 const W x = cut_window<W>(A, B, C, 2 * lane, P.bits);
                 const int li = jj * 32 + lane;
                 if (li < m_sub) {
@@ -236,20 +241,20 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
                 const int j = j0 + jj;
                 const int li = jj * 32 + lane;
                 uint32_t bal = 0;
-                if (P.canonical) bal = __shfl_sync(0xffffffffu, my_bal, j);
+                if (CANON) bal = __shfl_sync(0xffffffffu, my_bal, j);
                 if (li < m_sub) {
                     const uint32_t dr = wm.u.st.dr[li], d = dr >> 12, r = dr & 4095u;
                     W* const dst = wm.dst[d];
                     if (dst) st_word_plain(dst + r, wm.u.st.word[li]);
                     const uint32_t kidx = (uint32_t)(kbase + 32 * j + lane);
                     uint32_t slot = kidx;
-                    if (P.canonical) {
+                    if (CANON) {
                         const uint32_t fb = fwd_before + __popc(bal & lanemask_lt());
                         slot = ((bal >> lane) & 1u) ? fb : nfwd_total + (kidx - fb);
                     }
                     opos[slot] = wm.pos0[d] + r;
                 }
-                fwd_before += __popc(bal);
+                if (CANON) fwd_before += __popc(bal);
             }
             __syncwarp();   // the staging area is reused by the next unit
         }
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
             Suf s;
             split_key<W, Suf>(word, P, prefix, s);
             const uint32_t k32 = key32<Suf>(s, P.suffix_bits);
-            bool present = active && ix.nb != 0;
+            bool present = active && ix.nb != 0 && (prefix >> P.prefix_bits) == 0;   // anything that is not a word of this set (a corrupted buffer) is absent, not a wild read
             const uint2 de = ldg_keep(ix.dir + (present ? (prefix >> 5) : 0u));
             const uint32_t bit = prefix & 31;
             const uint32_t rank = de.y + __popc(de.x & ((1u << bit) - 1u));

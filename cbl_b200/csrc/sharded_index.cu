@@ -45,22 +45,30 @@ uint64_t splitmix(uint64_t& s) {
     return z ^ (z >> 31);
 }
 
-// world - 1 splitters s.t. each range holds ~1/world of the sample's COST: the cost of a word rises linearly from 1 at the
-// low end of the sorted prefix sample to tail_cost at mass quantile `knee` and stays there (the shorter the leading zero
-// run of a necklace, the less exact the probe's slot prediction; measured on 8 x B200, see sharded.py / DESIGN.md)
-std::vector<uint32_t> equal_cost_splitters(std::vector<uint32_t> pre, int world, double tail_cost = 1.5, double knee = 0.625) {
+// world - 1 splitters s.t. each range holds ~1/world of the sample's COST (the owner-side probe time, not the word count).
+// Relative cost of a word as a piecewise-linear function of the mass quantile of its prefix in the sorted sample: flat but
+// for the sparse tail of the prefix space (measured on B200 against the shards of an 8-GPU set, scripts/exp_shard_probe.py;
+// the same knots as PROBE_COST_KNOTS in cbl_b200/sharded.py)
+std::vector<uint32_t> equal_cost_splitters(std::vector<uint32_t> pre, int world) {
+    static const double KQ[] = {0.0, 0.625, 0.875, 0.9375, 1.0}, KW[] = {1.0, 1.0, 1.05, 1.12, 1.2};
     std::vector<uint32_t> sp;
     if (world <= 1 || pre.empty()) return sp;
     std::sort(pre.begin(), pre.end());
     const size_t n = pre.size();
-    const double a = (tail_cost - 1.0) / (2.0 * knee);
-    auto cum = [&](double q) { return q <= knee ? q + a * q * q : knee + a * knee * knee + tail_cost * (q - knee); };
-    const double total = cum(1.0);
+    const int GRID = 4096;
+    auto weight = [&](double q) {
+        int k = 0;
+        while (k < 3 && q > KQ[k + 1]) k++;
+        return KW[k] + (KW[k + 1] - KW[k]) * (q - KQ[k]) / (KQ[k + 1] - KQ[k]);
+    };
+    std::vector<double> cum(GRID + 1, 0.0);   // cumulative cost C(q) on a grid
+    for (int i = 1; i <= GRID; i++) cum[i] = cum[i - 1] + 0.5 * (weight((double)(i - 1) / GRID) + weight((double)i / GRID)) / GRID;
     for (int i = 1; i < world; i++) {
-        const double c = total * i / world;
-        double q;
-        if (c <= cum(knee)) q = a == 0.0 ? c : (-1.0 + std::sqrt(1.0 + 4.0 * a * c)) / (2.0 * a);
-        else q = knee + (c - cum(knee)) / tail_cost;
+        const double c = cum[GRID] * i / world;
+        const int hi = (int)(std::upper_bound(cum.begin(), cum.end(), c) - cum.begin());   // cum[hi - 1] <= c < cum[hi]
+        const int lo = std::max(hi - 1, 0);
+        const double f = hi <= GRID && cum[hi] > cum[lo] ? (c - cum[lo]) / (cum[hi] - cum[lo]) : 0.0;
+        const double q = ((double)lo + f) / GRID;
         sp.push_back(pre[std::min<size_t>((size_t)(q * n), n - 1)]);
     }
     for (size_t i = 1; i < sp.size(); i++) if (sp[i] <= sp[i - 1]) sp[i] = sp[i - 1] + 1;   // strictly increasing
@@ -81,6 +89,11 @@ class ShardedIndex final : public IIndex {
     std::vector<void*> recv_;
     std::vector<uint8_t*> back_;
     uint64_t cap_ = 0;
+    // fused query (shard_query.cuh): final-count slots of device d (slot s written by device s), call counter, and whether
+    // the receive buffers may hold anything else than the 0xFF "no word here" pattern
+    std::vector<unsigned long long*> fin_;
+    uint32_t epoch_ = 0;
+    bool recv_dirty_ = true;
 
     static void not_for_sharded(const char* what) {
         throw Error(CBL_EINVAL, std::string(what) + " takes device pointers of ONE GPU and is not available on a sharded handle (use the host-buffer entry points)");
@@ -95,10 +108,13 @@ class ShardedIndex final : public IIndex {
             cudaSetDevice(dev_[d]);
             if (d < (int)recv_.size() && recv_[d]) cudaFree(recv_[d]);
             if (d < (int)back_.size() && back_[d]) cudaFree(back_[d]);
+            if (d < (int)fin_.size() && fin_[d]) cudaFree(fin_[d]);
         }
         recv_.assign(g_, nullptr);
         back_.assign(g_, nullptr);
+        fin_.assign(g_, nullptr);
         cap_ = 0;
+        recv_dirty_ = true;
     }
     void ensure_cap(uint64_t cap_words) {
         if (cap_words <= cap_) return;
@@ -110,8 +126,21 @@ class ShardedIndex final : public IIndex {
             CUDA_CHECK(cudaSetDevice(dev_[d]));
             CUDA_CHECK(cudaMalloc(&recv_[d], (size_t)g_ * cap * wb_));
             CUDA_CHECK(cudaMalloc((void**)&back_[d], (size_t)g_ * cap));
+            CUDA_CHECK(cudaMalloc((void**)&fin_[d], 16 * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaMemset(fin_[d], 0, 16 * sizeof(unsigned long long)));
         }
         cap_ = cap;
+        recv_dirty_ = true;
+    }
+    // the fused query wants 0xFF wherever the receive buffers hold no word; it leaves them that way itself
+    void clean_recv() {
+        if (!recv_dirty_) return;
+        parallel(g_, [&](int d) {
+            CUDA_CHECK(cudaSetDevice(dev_[d]));
+            CUDA_CHECK(cudaMemsetAsync(recv_[d], 0xFF, (size_t)g_ * cap_ * wb_, sh_[d]->stream()));
+            CUDA_CHECK(cudaStreamSynchronize(sh_[d]->stream()));
+        });
+        recv_dirty_ = false;
     }
     void* recv_region(int owner, int src) const { return (uint8_t*)recv_[owner] + ((size_t)src * cap_) * wb_; }
     uint8_t* back_region(int src, int owner) const { return back_[src] + (size_t)owner * cap_; }
@@ -147,8 +176,8 @@ class ShardedIndex final : public IIndex {
     };
     static bool is_bad_byte(const Error& e) { return e.code == CBL_EINVAL && std::string(e.what()).find("non-ACGT") != std::string::npos; }
 
-    // route every group's words to their owners; returns false if the reads hold non-ACGT bytes (nothing useful was routed)
-    bool route_all(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, bool want_pos, std::vector<Group>& gr) {
+    // cut the batch into one group of records per device and copy every group to its device
+    void prepare_groups(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, bool want_pos, std::vector<Group>& gr) {
         const std::vector<size_t> cut = cut_records(offsets, n_seqs);
         gr.assign(g_, Group());
         uint64_t k0 = 0, n_max = 0;
@@ -164,7 +193,6 @@ class ShardedIndex final : public IIndex {
             G.counts.assign(g_, 0);
         }
         ensure_cap((uint64_t)((double)n_max / g_ * 1.3) + 4096);
-        std::atomic<bool> bad{false};
         parallel(g_, [&](int d) {   // copy in (once; the buffers survive a retry with larger regions)
             Group& G = gr[d];
             CUDA_CHECK(cudaSetDevice(dev_[d]));
@@ -174,7 +202,13 @@ class ShardedIndex final : public IIndex {
             if (G.n_bytes) CUDA_CHECK(cudaMemcpyAsync(G.d_seq, seq + offsets[cut[d]], G.n_bytes, cudaMemcpyHostToDevice, st));
             CUDA_CHECK(cudaStreamSynchronize(st));
         });
+    }
+    // route every group's words to their owners; returns false if the reads hold non-ACGT bytes (nothing useful was routed)
+    bool route_all(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, bool want_pos, std::vector<Group>& gr) {
+        prepare_groups(seq, offsets, n_seqs, want_pos, gr);
+        std::atomic<bool> bad{false};
         for (;;) {
+            recv_dirty_ = true;
             parallel(g_, [&](int d) {
                 Group& G = gr[d];
                 if (G.off.size() <= 1) return;
@@ -192,6 +226,49 @@ class ShardedIndex final : public IIndex {
             uint64_t mx = 0;
             for (auto& G : gr) for (uint64_t c : G.counts) mx = std::max(mx, c);
             if (mx <= cap_) return true;
+            ensure_cap((uint64_t)(mx * 1.1) + 4096);   // a region overflowed (nothing past cap was written): everybody again
+        }
+    }
+    // contains_seq of every group as the fused query (one kernel per device, running together: the words travel to their
+    // owners and the answers back over NVLink while the kernels run); returns false if the reads hold non-ACGT bytes
+    bool fused_query_all(const uint8_t* seq, const uint64_t* offsets, size_t n_seqs, std::vector<Group>& gr) {
+        prepare_groups(seq, offsets, n_seqs, true, gr);
+        std::atomic<bool> bad{false};
+        for (;;) {
+            clean_recv();
+            epoch_ = epoch_ % 65535 + 1;
+            recv_dirty_ = true;   // until the call has come back clean
+            parallel(g_, [&](int d) {
+                Group& G = gr[d];
+                std::vector<void*> mine(g_), theirs(g_);
+                std::vector<unsigned long long*> my_final(g_);
+                std::vector<const unsigned long long*> their_final(g_);
+                std::vector<uint8_t*> ans(g_);
+                for (int o = 0; o < g_; o++) {
+                    mine[o] = recv_region(o, d);          // my region at owner o
+                    my_final[o] = fin_[o] + d;            // my slot at owner o
+                    theirs[o] = recv_region(d, o);        // the region source o writes here
+                    their_final[o] = fin_[d] + o;
+                    ans[o] = back_region(o, d);           // my region in source o's answer buffer
+                }
+                FusedQuery q;
+                q.splitters = split_.data(); q.n_split = (uint32_t)split_.size();
+                q.peer_region = mine.data(); q.peer_final = my_final.data();
+                q.cap = cap_; q.d_pos = G.d_pos;
+                q.recv_region = theirs.data(); q.answer_region = ans.data(); q.final_ = their_final.data();
+                q.epoch = epoch_;
+                q.grid_share = (uint32_t)std::count(dev_.begin(), dev_.end(), dev_[d]);
+                try {
+                    sh_[d]->seq_contains_fused_dev((const uint8_t*)G.d_seq, G.n_bytes, G.off.data(), G.off.size() - 1, q, G.counts.data());
+                } catch (const Error& e) {
+                    if (!is_bad_byte(e)) throw;
+                    bad = true;   // the kernel has run to its end all the same: the other devices are not left waiting
+                }
+            });
+            if (bad) return false;
+            uint64_t mx = 0;
+            for (auto& G : gr) for (uint64_t c : G.counts) mx = std::max(mx, c);
+            if (mx <= cap_) { recv_dirty_ = false; return true; }
             ensure_cap((uint64_t)(mx * 1.1) + 4096);   // a region overflowed (nothing past cap was written): everybody again
         }
     }
@@ -334,15 +411,7 @@ public:
         if (n_seqs == 0) return;
         std::vector<Group> gr;
         struct Free { ShardedIndex* s; std::vector<Group>* g; ~Free() { s->free_groups(*g); } } fr{this, &gr};
-        if (route_all(seq, offsets, n_seqs, true, gr)) {
-            parallel(g_, [&](int o) {   // owner o probes region s of its receive buffer into ITS region of device s's answer buffer: one launch
-                std::vector<const void*> seg(g_);
-                std::vector<uint64_t> n(g_);
-                std::vector<uint8_t*> dst(g_);
-                for (int s = 0; s < g_; s++) { seg[s] = recv_region(o, s); n[s] = gr[s].counts[o]; dst[s] = back_region(s, o); }
-                sh_[o]->words_contains_segments_dev(seg.data(), n.data(), dst.data(), (uint32_t)g_);
-                sh_[o]->sync();
-            });
+        if (fused_query_all(seq, offsets, n_seqs, gr)) {
             parallel(g_, [&](int d) {   // every answer has landed: into read order, out to the host
                 Group& G = gr[d];
                 if (!G.n_kmers) return;

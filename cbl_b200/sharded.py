@@ -72,32 +72,40 @@ def exchange(send: torch.Tensor, send_counts: torch.Tensor, group=None):
     return recv, recv_counts
 
 
-def equal_mass_splitters(prefixes: torch.Tensor, world: int, tail_cost: float = 1.0, knee: float = 0.625) -> torch.Tensor:
-    """world-1 splitters s.t. each range [s_{i-1}, s_i) holds ~1/world of the sample's COST.
+# Relative probe cost of a word as a function of the mass quantile q of its prefix in the sorted sample, as (q, weight)
+# knots of a piecewise-linear curve: flat except for the sparse tail of the prefix space (few suffixes per bucket, bucket
+# tables spread over most of the prefix range).  Measured on B200, K=25: (a) word-level probe against the shard one rank
+# of an 8-GPU run holds (scripts/exp_shard_probe.py: 500 M k-mers of 4 G in one eighth of the prefix mass, arrival order):
+# 19.6, 19.8, 20.2, 20.9 and 23.7 ms per 1 G words in octiles 0, 2, 4, 6 and 7; (b) the fused query on 8 x B200 with
+# equal-mass splitters: ranks 0-4 finish their share together, ranks 5 and 6 1-2 ms later, rank 7 7 ms later; with a
+# tail weight of 1.25 rank 7 is 3.6 ms early: the knots below put it in between.  Before the correction bytes were scaled
+# by bucket size (index_view.cuh sub_scale) measurement (a) rose from 20.3 to 30.3 ms: a plain signed byte saturates in
+# the large, structured buckets of an 8-GPU set.
+PROBE_COST_KNOTS = ((0.0, 1.0), (0.625, 1.0), (0.875, 1.05), (0.9375, 1.12), (1.0, 1.2))
 
-    With ``tail_cost == 1`` cost = mass (every word counts 1).  Measured on 8 x B200 with equal-mass splitters (K=25,
-    500 M k-mers per rank, 1.06 G look-ups per rank and step): the owner-side probe takes 22 ns per 1000 words on rank 0
-    and grows steadily to 34 ns on ranks 5-7 — the shorter the leading zero run of a necklace, the more structure its
-    suffixes have and the less exact the slot prediction (more suffix windows per look-up).  The model used here: the
-    cost of a word rises linearly from 1 at the low end of the sorted sample to ``tail_cost`` at mass quantile ``knee``
-    and stays there; the splitters equalise cost, not count."""
+
+def equal_mass_splitters(prefixes: torch.Tensor, world: int, tail_cost: Optional[float] = None, knee: float = 0.625,
+                         knots: Optional[Sequence] = None) -> torch.Tensor:
+    """world-1 splitters s.t. each range [s_{i-1}, s_i) holds ~1/world of the sample's COST: the splitters equalise the
+    owner-side probe time, not the word count.
+
+    ``knots``: (mass quantile, relative cost) points of a piecewise-linear cost curve over the sorted sample (default
+    ``PROBE_COST_KNOTS``; ``((0, 1), (1, 1))`` = plain equal mass).  ``tail_cost`` (legacy two-piece model, what
+    CBL_SPLIT_TAIL_COST sets): cost rising linearly from 1 at q = 0 to ``tail_cost`` at ``knee``, constant beyond."""
     if world == 1:
         return prefixes.new_empty(0)
+    if tail_cost is not None:
+        knots = ((0.0, 1.0), (knee, tail_cost), (1.0, tail_cost))
+    elif knots is None:
+        knots = PROBE_COST_KNOTS
     srt, _ = torch.sort(prefixes)
     n = srt.numel()
-    a = (tail_cost - 1.0) / (2.0 * knee)            # cumulative cost C(q) = q + a q^2 (q <= knee), linear beyond
-
-    def cum(q):
-        return q + a * q * q if q <= knee else knee + a * knee * knee + tail_cost * (q - knee)
-
-    total = cum(1.0)
+    grid = np.linspace(0.0, 1.0, 4097)
+    w = np.interp(grid, [k[0] for k in knots], [k[1] for k in knots])
+    cum = np.concatenate([[0.0], np.cumsum((w[1:] + w[:-1]) * 0.5 * np.diff(grid))])   # cumulative cost C(q)
     idx = []
     for i in range(1, world):
-        c = total * i / world
-        if c <= cum(knee):
-            q = c if a == 0.0 else (-1.0 + (1.0 + 4.0 * a * c) ** 0.5) / (2.0 * a)
-        else:
-            q = knee + (c - cum(knee)) / tail_cost
+        q = float(np.interp(cum[-1] * i / world, cum, grid))
         idx.append(min(int(q * n), n - 1))
     sp = srt[torch.tensor(idx, device=srt.device)]
     # strictly increasing splitters keep every range non-empty in prefix space
@@ -335,8 +343,9 @@ class ShardedCBL:
             if self.world > 1:
                 if self.rank == 0:
                     w = self.engine.sample_words(sample_bases, seed=20240229)
+                    tc = os.environ.get("CBL_SPLIT_TAIL_COST")   # developer knob: the legacy two-piece cost model
                     sp.copy_(equal_mass_splitters(word_prefixes(w, self.suffix_bits, prefix_bits), self.world,
-                                                   tail_cost=float(os.environ.get("CBL_SPLIT_TAIL_COST", self.TAIL_COST_BY_WORLD.get(self.world, self.TAIL_COST)))))
+                                                   tail_cost=float(tc) if tc else None))
                 ctrl = sp.cpu() if dist.get_backend(group) == "gloo" else sp   # gloo: control traffic on CPU tensors
                 dist.broadcast(ctrl, src=0, group=group)
                 sp = ctrl.to(self.device)
@@ -401,14 +410,7 @@ class ShardedCBL:
                 return C, pos
             cap = int(int(C.max()) * 1.1) + 4096                     # a region overflowed somewhere: everybody retries
 
-    # Relative probe cost of a word beyond the knee of the sorted prefix sample (equal_mass_splitters).  Measured with the
-    # single-launch owner-side probe, 1 G look-ups per rank against 500 M k-mers per rank: on 8 x B200 the cost per 1000
-    # words climbs from 19.8 ns on rank 0 to 29.0 ns on ranks 5-7 (x1.5: buckets of the 4 G-k-mer set are 4x larger and the
-    # slot prediction in the structured high-prefix buckets needs more windows); on 2 x B200 it is 18.3 vs 19.9 ns (x1.1).
-    TAIL_COST_BY_WORLD = {1: 1.0, 2: 1.1, 3: 1.3}
-    TAIL_COST = 1.5
-
-    SLACK = 1.3    # region capacity over the even share (cost-weighted splitters give the first rank ~20 % more words)
+    SLACK = 1.3    # region capacity over the even share (cost-weighted splitters give the first ranks a few % more words)
 
     def _mutate(self, op: int, d_buf: int, offsets: np.ndarray) -> None:
         if self.peer is not None:
@@ -504,6 +506,8 @@ class ShardedCBL:
                 final_counts=[px.final_slot(px.own_ctrl, s_) for s_ in range(g)],
                 epoch=epoch)
             C = px.all_counts(counts)                                # barrier: every consumer is done => my answers have landed
+            if os.environ.get("CBL_SHARD_TRACE"):
+                print(f"[shard trace] rank {self.rank}: sent {int(C[self.rank].sum())} words, received {int(C[:, self.rank].sum())}", flush=True)
             if int(C.max()) <= px.cap:
                 px.recv_dirty = False                                # every word that arrived was consumed and its slot reset
                 break

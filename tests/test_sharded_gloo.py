@@ -43,9 +43,17 @@ def test_word_prefixes_and_route():
     dest, order, counts = route(pre, sp)
     assert dest.tolist() == [1, 0, 2, 1, 1, 1, 0, 2] and counts.tolist() == [2, 4, 2]
     assert pre[order].tolist() == [1, 0, 5, 3, 3, 7, 9, 9]  # stable grouping
-    s = equal_mass_splitters(torch.arange(1000), 4)
+    flat = ((0.0, 1.0), (1.0, 1.0))
+    s = equal_mass_splitters(torch.arange(1000), 4, knots=flat)
     assert s.tolist() == [250, 500, 750]
     assert equal_mass_splitters(torch.zeros(100, dtype=torch.int64), 3).tolist() == [0, 1]
+    # default: the measured probe-cost curve (PROBE_COST_KNOTS), ranges equalise its integral: the last range is the shortest
+    from cbl_b200.sharded import PROBE_COST_KNOTS
+    d = equal_mass_splitters(torch.arange(80000), 8)
+    edges = [0] + d.tolist() + [80000]
+    qs, ws = [k[0] for k in PROBE_COST_KNOTS], [k[1] for k in PROBE_COST_KNOTS]
+    cost = [sum(float(np.interp(x / 80000.0, qs, ws)) for x in range(a, b)) for a, b in zip(edges, edges[1:])]
+    assert max(cost) - min(cost) <= 0.002 * max(cost) and edges[1] > 10000 > edges[-1] - edges[-2]
     # cost-weighted splitters: cost rises from 1 to 1.5 over the first 62.5 % of the sorted sample, ranges equalise cost
     w = equal_mass_splitters(torch.arange(8000), 8, tail_cost=1.5)
     edges = [0] + w.tolist() + [8000]
