@@ -734,12 +734,18 @@ def run_config2(args):
     # streaming branch of SURVEY 8d's min().
     dom = None
     for name, rec_ in prof.items():
-        if "seq_words_kernel" in name and (dom is None or rec_["ms"] > prof[dom]["ms"]):
+        if ("seq_words_kernel" in name or "shard_query_kernel" in name) and (dom is None or rec_["ms"] > prof[dom]["ms"]):
             dom = name
     roof = None
     if dom:
         ms_per_launch = prof[dom]["ms"] / max(1, prof[dom]["n"])
         bytes_per_kmer = 1 + 1 + 8 + 8 + 2 + 32
+        fused_sharded = "shard_query_kernel" in dom
+        if fused_sharded:
+            # the fused sharded query also moves every word once out (8 B store into the owner's region: remote HBM for 7 of 8
+            # words, but every GPU receives as much as it sends), once in (8 B) and resets its slot (8 B), and writes the 4-byte
+            # answer slot of every k-mer for the gather that follows
+            bytes_per_kmer += 8 + 8 + 8 + 4
         kmers_per_launch = n_q_kmers / max(1, prof[dom]["n"])
         achieved = bytes_per_kmer * kmers_per_launch / (ms_per_launch * 1e-3) / 1e9
         stream_bpk = 8 + 1 + 8 + min(stored * 4 / max(1, n_q_kmers), math.ceil(math.log2(stored / max(1, nb) + 1)) * 32)
@@ -757,7 +763,8 @@ def run_config2(args):
                 "algorithmic_bytes_per_kmer": bytes_per_kmer, "algorithmic_bytes_per_launch": bytes_per_kmer * kmers_per_launch,
                 "traffic_source": traffic_src,
                 "model": "1 B ASCII + 1 B answer + 8 B directory word + 8 B bucket range + 2 B corrections + one 32 B suffix window per k-mer "
-                         "(realised branch of SURVEY 8d's probe figure: unsorted queries, random lookups)",
+                         "(realised branch of SURVEY 8d's probe figure: unsorted queries, random lookups)"
+                         + (" + 8 B word out + 8 B word in + 8 B slot reset + 4 B answer slot (fused sharded query: shard_query.cuh)" if fused_sharded else ""),
                 "frac_vs_sec8d_streaming_bound": stream_bpk * kmers_per_launch / (ms_per_launch * 1e-3) / 1e9 / peak,
                 "sec8d_streaming_bytes_per_kmer": stream_bpk,
                 "note": "instruction-issue bound (518 thread-instructions per k-mer: necklace ~250, probe ~270), not HBM-byte bound; the 60 % "
@@ -793,7 +800,26 @@ def run_config2(args):
         assert int(ha.sum(dtype=np.int64)) == hits, "e2e answers differ from the device-resident run"
         e2e = {"value": total_q * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(query.numel()) * world,
                "d2h_bytes_per_step": int(n_q_kmers) * world, "ms_per_step": 1e3 * t_e2e / args.steps}
-        del h_query, h_ans
+        # what the host links allow: the same bytes copied in and out by every rank at the same time, nothing else running
+        # (two streams, pinned memory).  e2e cannot beat this; on a box whose GPUs share host bandwidth it is what limits e2e at N > 1
+        d_in, d_out = torch.empty_like(query), torch.empty(n_q_kmers, dtype=torch.uint8, device=device)
+        s_a, s_b = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            with torch.cuda.stream(s_a):
+                d_in.copy_(h_query, non_blocking=True)
+            with torch.cuda.stream(s_b):
+                h_ans.copy_(d_out, non_blocking=True)
+        s_a.synchronize()
+        s_b.synchronize()
+        barrier()
+        t_link = max_over_ranks(time.perf_counter() - t0)
+        e2e["host_link_floor"] = {"ms_per_step": 1e3 * t_link / args.steps,
+                                  "GBps_all_ranks_both_directions": (int(query.numel()) + int(n_q_kmers)) * world * args.steps / t_link / 1e9,
+                                  "what": "pure H2D + D2H of the step's bytes on every rank at once (pinned memory, two streams): the floor of e2e on this box"}
+        del h_query, h_ans, d_in, d_out
 
     # ---- parity_check: the built set and the step's own answers against the oracle (every rank)
     parity = None

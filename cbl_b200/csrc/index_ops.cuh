@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) build_sub_kernel(IndexView<Suf> ix, int s
                 if (key32<Suf>(ix.suf[mid], suffix_bits) < kb) lo = mid + 1; else hi = mid;
             }
             dv = (int)(lo - start) - (int)__umulhi(kb, end - start);
-            const int sc = sub_scale(end - start);   // stored in units of 2^sc slots (rounded to nearest)
+            const int sc = sub_scale(ss.eb);   // stored in units of 2^sc slots (rounded to nearest)
             dv = (dv + ((1 << sc) >> 1)) >> sc;
             dv = min(max(dv, -127), 127);
         }

@@ -261,20 +261,15 @@ __device__ __forceinline__ ProbeResult probe_key(const IndexView<Suf>& ix, const
 constexpr int SUB_SHIFT = CBL_SUB_SHIFT;
 constexpr int SUB_GROUP = 1 << SUB_SHIFT;
 
-// Corrections are stored in units of 2^sub_scale(span) slots, so that the signed byte covers a deviation of up to a quarter
-// .. a half of the bucket whatever its size (a plain byte saturates at 127 slots: in buckets of thousands of suffixes
-// whose distribution is far from uniform — necklace words with few leading zeros — the clamped prediction then misses by
-// hundreds of slots and the lookup pays window after window).  The unit depends on the bucket size only: nothing to store.
-#ifndef CBL_SUB_SCALED
-#define CBL_SUB_SCALED 1
+// Corrections are stored in units of 2^sc slots, sc = sub_scale(eb) growing with the bucket (eb = log2 of its number of
+// correction slots), so that the signed byte covers a deviation of a fixed fraction of the bucket whatever its size (a
+// plain byte saturates at 127 slots: in buckets of thousands of suffixes whose distribution is far from uniform — necklace
+// words with few leading zeros — the clamped prediction then misses by hundreds of slots and the lookup pays window
+// after window).  The unit depends on the bucket size only: nothing to store, two instructions to compute.
+#ifndef CBL_SUB_SCALE_BIAS
+#define CBL_SUB_SCALE_BIAS 4     // 99: plain bytes (developer A/B)
 #endif
-__device__ __forceinline__ int sub_scale(uint32_t span) {
-#if CBL_SUB_SCALED
-    return max(0, 23 - (int)__clz(span | 1u));   // floor(log2(span)) - 8
-#else
-    return 0;
-#endif
-}
+__device__ __forceinline__ int sub_scale(int eb) { return min(max(eb - CBL_SUB_SCALE_BIAS, 0), 8); }
 struct SubSlots {
     uint32_t first;  // index of the bucket's first slot in sub[]
     int eb;          // log2 of the number of boundaries kept (0 => no correction for this bucket)
@@ -311,9 +306,9 @@ __device__ __forceinline__ uint32_t predict_slot(const int8_t* __restrict__ sub,
     int d1 = ldg_keep(sub + ss.first + j + 1);
 #endif
     d1 = (j + 1 < (1u << ss.eb)) ? d1 : 0;
-    const int sc = sub_scale(span);
+    const int sc = sub_scale(ss.eb);
     const int v = d0 * 256 + (d1 - d0) * frac;   // interpolated correction in 1/256 of a unit of 2^sc slots
-    const int corr = ss.eb > 0 ? (sc < 8 ? (v + (128 >> sc)) >> (8 - sc) : v << (sc - 8)) : 0;
+    const int corr = ss.eb > 0 ? (v + (128 >> sc)) >> (8 - sc) : 0;
     const int guess = (int)__umulhi(k32, span) + corr;
     return (uint32_t)min(max(guess, 0), max((int)span - 1, 0));
 }

@@ -132,6 +132,9 @@ template <> __device__ __forceinline__ u128 cut_window<u128>(uint64_t A, uint64_
 // words, bucket ranges, correction bytes, suffix windows), each stage issuing U independent loads.
 // Measured on B200: U = 1 with high occupancy (40 registers) beats U = 2 / 4 (80 / 120 registers);
 // only U = 1 is instantiated.
+#ifndef CBL_SW_OPAQUE_IDS
+#define CBL_SW_OPAQUE_IDS 1
+#endif
 #ifndef CBL_SW_MIN_BLOCKS_WORDS
 #define CBL_SW_MIN_BLOCKS_WORDS 24   // word-level probe (MODE 3): 32 blocks (32 registers, no spills) measured 24.4 vs 19.3 ms: more warps thrash L1/L2
 #endif
@@ -174,14 +177,26 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN
     __shared__ __align__(16) uint8_t s_flags[PROBE ? CHUNK_KMERS : 16];
     __shared__ uint4 q_a[2][QN];                 // {L, R, g, span}
     __shared__ PendingKey<Suf> q_b[2][QN];       // {suffix, slot | rounds << 16}
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // lane / warp index as opaque register values in the probing modes: derived from threadIdx.x they are rematerialised
+    // (special-register read + shift / mask) at nearly every shared-memory access under the 40-register budget
+    int lane, warp;
+#if CBL_SW_OPAQUE_IDS
+    if (PROBE) {
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+        asm volatile("{\n .reg .u32 t;\n mov.u32 t, %%tid.x;\n shr.u32 %0, t, 5;\n}" : "=r"(warp));
+    } else
+#endif
+    {
+        lane = threadIdx.x & 31;
+        warp = threadIdx.x >> 5;
+    }
     uint32_t q_head = 0, q_count = 0;  // warp-uniform
 
     // enqueue the lanes with `und` set (warp-collective)
     auto q_push = [&](bool und, Suf s, uint32_t L, uint32_t R, uint32_t g, uint32_t span, uint32_t slot_it) {
         const uint32_t bal = __ballot_sync(0xffffffffu, und);
         if (und) {
-            const uint32_t i = (q_head + q_count + __popc(bal & lanemask_lt())) & (QN - 1);
+            const uint32_t i = (q_head + q_count + __popc(bal & ((1u << lane) - 1u))) & (QN - 1);
             q_a[warp][i] = make_uint4(L, R, g, span);
             PendingKey<Suf> pk;
             pk.s = s;
@@ -311,7 +326,7 @@ __global__ void __launch_bounds__(SW_THREADS, (MODE == 3 && U == 1) ? CBL_SW_MIN
                 }
                 if (P.canonical) {
                     const uint32_t bal = s_fwd[warp][j];
-                    const uint32_t fb = fwd_before + __popc(bal & lanemask_lt());
+                    const uint32_t fb = fwd_before + __popc(bal & ((1u << lane) - 1u));
                     const bool is_fwd = (bal >> lane) & 1;
                     slot[u] = is_fwd ? fb : nfwd_total + ((uint32_t)kidx - fb);
                     fwd_before += __popc(bal);

@@ -37,6 +37,9 @@ constexpr int SQ_UNIT = 256;     // words staged per flush (8 rounds of 32 k-mer
 constexpr int SQ_BLOCK = 1024;   // words per consumer block = granularity of the ready counters
 constexpr int SQ_HALF = 1024;    // k-mers per produce task: half a reference chunk, lane l packs bases [32 l, 32 l + 32)
 constexpr int SQ_MAX_RANKS = ROUTE_MAX_SPLIT + 1;
+#ifndef CBL_SQ_OPAQUE_IDS
+#define CBL_SQ_OPAQUE_IDS 1
+#endif
 #ifndef CBL_SQ_MIN_BLOCKS
 #define CBL_SQ_MIN_BLOCKS 24     // same residency as the single-GPU fused probe
 #endif
@@ -128,7 +131,18 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
     constexpr int QN = PENDING_CAP;
     __shared__ SqWarpMem<W, Suf> s_w[SQ_THREADS / 32];
     __shared__ uint32_t s_split[16];
-    const int lane = threadIdx.x & 31;
+    // lane and warp index as opaque register values: derived from threadIdx.x the compiler re-reads the special register and
+    // redoes the shift / multiply at nearly every shared-memory access under this kernel's register pressure (measured: 5 %
+    // of all instructions); an asm volatile result cannot be rematerialised
+    int lane;
+    uint32_t widx;
+#if CBL_SQ_OPAQUE_IDS
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("{\n .reg .u32 t;\n mov.u32 t, %%tid.x;\n shr.u32 %0, t, 5;\n}" : "=r"(widx));
+#else
+    lane = threadIdx.x & 31;
+    widx = threadIdx.x >> 5;
+#endif
     if (threadIdx.x < 16) {
         s_split[threadIdx.x] = threadIdx.x < ROUTE_MAX_SPLIT ? a.split[threadIdx.x] : 0xFFFFFFFFu;
         s_w[0].cnt[threadIdx.x] = 0;
@@ -136,7 +150,7 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) a.err[2] = sq_now_ns();
     __syncthreads();   // the only block-level barrier: from here on the two warps are independent
-    SqWarpMem<W, Suf>& wm = s_w[threadIdx.x >> 5];
+    SqWarpMem<W, Suf>& wm = s_w[widx];
 
     // ---- produce task t: half `t & 1` of chunk `t >> 1` ---------------------------------------------------------
     auto produce = [&](uint32_t task) {
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
                     const uint32_t kidx = (uint32_t)(kbase + 32 * j + lane);
                     uint32_t slot = kidx;
                     if (CANON) {
-                        const uint32_t fb = fwd_before + __popc(bal & lanemask_lt());
+                        const uint32_t fb = fwd_before + __popc(bal & ((1u << lane) - 1u));
                         slot = ((bal >> lane) & 1u) ? fb : nfwd_total + (kidx - fb);
                     }
                     opos[slot] = wm.pos0[d] + r;
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
     auto q_push = [&](bool und, Suf s, uint32_t L, uint32_t R, uint32_t g, uint32_t span, uint32_t slot_it) {
         const uint32_t bal = __ballot_sync(0xffffffffu, und);
         if (und) {
-            const uint32_t i = (q_head + q_count + __popc(bal & lanemask_lt())) & (QN - 1);
+            const uint32_t i = (q_head + q_count + __popc(bal & ((1u << lane) - 1u))) & (QN - 1);
             wm.u.pr.q_a[i] = make_uint4(L, R, g, span);
             PendingKey<Suf> pk;
             pk.s = s;
