@@ -838,19 +838,31 @@ def run_config2(args):
                "sample": r["sample"], "note": r["kind_note"], "contains_seq_kmers_per_s": r["contains_kmers_per_s"],
                "insert_seq_kmers_per_s": r["insert_kmers_per_s"], "host_cores_available": os.cpu_count()}
 
+    # NVLink traffic of the fused sharded query: 8-byte words out to the other owners, 1-byte answers back, over the kernel's time
+    nvlink = None
+    C = getattr(cbl, "last_route_counts", None) if world > 1 else None
+    if C is not None and dom and "shard_query_kernel" in dom:
+        sent_away = int(C[rank].sum()) - int(C[rank][rank])
+        recv_from_others = int(C[:, rank].sum()) - int(C[rank][rank])
+        k_ms = prof[dom]["ms"] / max(1, prof[dom]["n"])
+        nvlink = {"words_out": sent_away, "answers_out": recv_from_others,
+                  "egress_GBps": (sent_away * 8 + recv_from_others) / (k_ms * 1e-3) / 1e9,
+                  "ingress_GBps": (recv_from_others * 8 + sent_away) / (k_ms * 1e-3) / 1e9,
+                  "kernel_ms": k_ms, "rank": rank,
+                  "what": "rank 0 over its fused query kernel: 8-byte word stores to the other owners + 1-byte answers back (NVLink 5 / NVSwitch: 900 GB/s per direction)"}
     if rank == 0:
         insert_block = {"value": insert_value, "unit": UNIT, "steps": n_ins_steps, "ms_per_step": 1e3 * ins_elapsed / n_ins_steps,
                         "wall_ms_per_step": 1e3 * float(np.mean(ins_wall)), "first_build_s_cold_arena": t_build_first, "e2e": ins_e2e,
                         "kernel_ms": build_prof, "kernel_ms_sum": sum(v["ms"] for v in build_prof.values()) if build_prof else None,
                         "roofline": build_roof, "gpu_launches": launches_ins,
                         "what": "one step = insert_seq of the whole index (500 x 1 Mbp per GPU) into a fresh empty set, reads resident in HBM"}
-        contains_block = {"value": value, "ms_per_step": 1e3 * elapsed / args.steps, "e2e": e2e}
+        contains_block = {"value": value, "ms_per_step": 1e3 * elapsed / args.steps, "e2e": e2e, "nvlink": nvlink}
         cfg = {"workload": "configs[1]: contains_seq of 1 Gbp synthetic FASTA vs 500M-k-mer index, K=25, T=u64, PREFIX_BITS=24"
                            + (" — headline = the index build (insert_seq)" if insert_headline else ""),
                "index_records": len(i_off) - 1, "query_records": len(q_off) - 1, "record_bp": rec, "per_gpu": world > 1,
                "stored_kmers": stored, "buckets": nb, "hit_fraction": hits / max(1, n_q_kmers),
                "l2_policy": f"inputs larger than L2: {query.numel() / 1e6:.0f} MB query + {stored * 4 / 1e6:.0f} MB index per step",
-               "parallelism": "1 GPU" if world == 1 else f"prefix-range sharded x{world}, fused route over NVLink peer memory"}
+               "parallelism": "1 GPU" if world == 1 else f"prefix-range sharded x{world}, one fused route + probe kernel per GPU over NVLink peer memory"}
         line = {
             "metric": metric_name(2, args.metric), "value": insert_value if insert_headline else value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup,

@@ -1089,7 +1089,15 @@ public:
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         if (n == 0) return;
         std::vector<W> h(n);
-        for (size_t i = 0; i < n; i++) h[i] = sizeof(W) == 16 ? (W)(((u128)(hi ? hi[i] : 0) << 64) | lo[i]) : (W)lo[i];
+        const int key_bits = P_.bits + P_.pos_bits;
+        for (size_t i = 0; i < n; i++) {
+            h[i] = sizeof(W) == 16 ? (W)(((u128)(hi ? hi[i] : 0) << 64) | lo[i]) : (W)lo[i];
+            // a mutation must not be fed anything that is not the word of a k-mer: the merge uses the all-ones word as its
+            // exhausted-side sentinel and the directory is sized for PREFIX_BITS-bit prefixes (a membership test just answers no)
+            const bool too_wide = key_bits < (int)(8 * sizeof(W)) && (h[i] >> key_bits) != 0;
+            if (op != 0 && (too_wide || h[i] == ~(W)0))
+                throw Error(CBL_EINVAL, "word " + std::to_string(i) + " is not the word of a k-mer (wider than 2K + POS_BITS bits, or all ones)");
+        }
         DevBuf<W> d(n, st_);
         DevBuf<uint8_t> flags(n, st_);
         CUDA_CHECK(cudaMemcpyAsync(d.get(), h.data(), n * sizeof(W), cudaMemcpyHostToDevice, st_));

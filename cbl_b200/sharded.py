@@ -510,6 +510,7 @@ class ShardedCBL:
                 print(f"[shard trace] rank {self.rank}: sent {int(C[self.rank].sum())} words, received {int(C[:, self.rank].sum())}", flush=True)
             if int(C.max()) <= px.cap:
                 px.recv_dirty = False                                # every word that arrived was consumed and its slot reset
+                self.last_route_counts = C                           # C[s][d] = words rank s sent to owner d (bench: NVLink traffic)
                 break
             cap = int(int(C.max()) * 1.1) + 4096                     # a region overflowed somewhere: everybody refills and retries
         if n:

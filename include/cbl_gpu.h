@@ -126,7 +126,9 @@ int32_t cbl_load_from_file(const cbl_t* proto, const char* path, cbl_t** out);
 /* words of the records, in the reference's order, left on the device: d_words = n_kmers * (8|16) bytes */
 int32_t cbl_seq_words_dev(cbl_t* h, const uint8_t* d_buf, const uint64_t* offsets, size_t n_seqs, void* d_words);
 /* op: 0 contains (d_out required), 1 insert, 2 remove (d_out optional = membership before the call);
- * d_out may be peer memory (the sharded path answers straight into the asking rank's buffer) */
+ * d_out may be peer memory (the sharded path answers straight into the asking rank's buffer).  The membership test accepts any
+ * bit pattern (what is not the word of a k-mer of this set is simply absent); insert / remove require words made by this
+ * library (cbl_seq_words_dev, cbl_export_words_dev, the route kernels): 2K + POS_BITS significant bits, never all ones. */
 int32_t cbl_words_op_dev(cbl_t* h, int32_t op, const void* d_words, size_t n, uint8_t* d_out);
 /* insert (1) / remove (2) the words of n_seg device segments as ONE batch (the per-source regions of a sharded receive
  * buffer): the shard is rewritten once, not once per segment */

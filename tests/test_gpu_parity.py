@@ -429,6 +429,26 @@ def test_route_and_gather(gpu, k, tb, pb):
             assert counts.min() > 0.8 * counts.max()  # equal-mass splitters balance random DNA
 
 
+def test_word_probe_tolerates_arbitrary_bit_patterns(gpu):
+    """cbl_words_op_dev(op = contains) with words that cannot come from a k-mer (all ones = the exchange buffers' "nothing
+    here" pattern, prefixes beyond 2^PREFIX_BITS, random bits): every answer is 0, nothing is read out of bounds."""
+    import torch
+
+    g = gpu.CBL(25, 64, 24)
+    g.insert_seq(util.random_dna(50_000, seed=3).tobytes())
+    rng = np.random.default_rng(9)
+    junk = rng.integers(-(2 ** 63), 2 ** 63 - 1, size=200_000, dtype=np.int64) | np.int64(-(2 ** 62))   # top bits set: wider than a word
+    junk[::7] = -1
+    real_lo, _ = g.words_arrays()
+    words = torch.from_numpy(np.concatenate([junk, real_lo[:1000].view(np.int64)])).cuda()
+    out = torch.full((words.numel(),), 7, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    g.words_op_dev(0, words.data_ptr(), words.numel(), out.data_ptr())
+    g.sync()
+    res = out.cpu().numpy()
+    assert not res[: len(junk)].any() and res[len(junk):].all()
+
+
 # ------------------------------------------------------------------------------------------------
 # non-ACGT bytes are dropped by filter_map while chunking stays on raw byte offsets
 # (src/kmer.rs:133-135, src/cbl.rs:239-289) — reproduced on the GPU by the sanitising slow path
