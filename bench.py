@@ -754,6 +754,8 @@ def run_config2(args):
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
+                if fused_sharded:
+                    tj = tj["fused_sharded"]   # captured on the 1-GPU test bed of the kernel (ncu cannot replay a multi-rank kernel)
                 traffic = tj["dram_bytes_per_kmer"] * kmers_per_launch
                 traffic_src = tj.get("source")
             except Exception:

@@ -80,6 +80,16 @@ __device__ __forceinline__ void st_word_plain(u128* p, u128 v) {
     *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2((unsigned long long)v, (unsigned long long)(v >> 64));   // one 16-byte store
 }
 
+// has the word of this slot landed?  An aligned 8-byte store arrives whole.  A 16-byte store is one transaction too, but the
+// memory model does not promise it: the high half of a 128-bit word always has zero top bits (2K + POS_BITS <= 125), so
+// "high half all ones" means not landed for sure, and "low half all ones under a landed high half" is either a torn pair or
+// (once in 2^64 words) a real value — wait a little, then take it
+__device__ __forceinline__ bool sq_missing(uint64_t w, uint32_t) { return w == ~0ull; }
+__device__ __forceinline__ bool sq_missing(u128 w, uint32_t spins) {
+    const uint64_t hi = (uint64_t)(w >> 64), lo = (uint64_t)w;
+    return hi == ~0ull || (lo == ~0ull && spins < 2000u);
+}
+
 __device__ __forceinline__ unsigned long long sq_now_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
             if (active) {
                 // stored by a peer moments ago (read past L1).  The block's last word has landed, so a word still missing here
                 // is in flight (reserved together with words that have arrived): wait for it
-                for (uint32_t spin = 0; word == sq_sentinel<W>(); spin++) {
+                for (uint32_t spin = 0; sq_missing(word, spin); spin++) {
                     if (spin > SQ_SPIN_MAX) { atomicExch(a.err + 1, 2ull); word = (W)0; break; }
                     __nanosleep(200);
                     word = ld_cg_word(in_words + idx);
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(SQ_THREADS, CBL_SQ_MIN_BLOCKS) shard_query_ker
         // is in flight (consume waits for a straggler)
         W last = sq_sentinel<W>();
         if (lane == 0) last = ld_cg_word(in_words + (m - 1));
-        if (__shfl_sync(0xffffffffu, (int)(last == sq_sentinel<W>()), 0)) return 0;
+        if (__shfl_sync(0xffffffffu, (int)sq_missing(last, 0u), 0)) return 0;
         return m;
     };
 

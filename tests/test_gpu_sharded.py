@@ -91,6 +91,18 @@ WORKER = textwrap.dedent(
         sh.remove_seqs_dev(r0.data_ptr(), np.array([0, K], dtype=np.uint64))
     ref.remove_seq(reads[0][:100000]); ref.remove_seq(reads[0][100000:])
     assert sh.count() == ref.count()
+    # a rank without reads still takes part in the query (it answers the words the others send it); the query after a
+    # mutation finds the exchange buffers used by another path and cleans them first
+    q = np.concatenate([reads[1][150000:260000], util.random_dna(40000, seed=77)])
+    qd = torch.from_numpy(q).to(dev)
+    if "fused" not in MODE:
+        pass
+    elif rank == 0:
+        got = sh.contains_seqs_dev(qd.data_ptr(), np.array([0, 70000, len(q)], dtype=np.uint64)).cpu().numpy()
+        exp = np.concatenate([ref.contains_seq(q[:70000]), ref.contains_seq(q[70000:])])
+        assert np.array_equal(got, exp) and 0 < got.sum() < len(got)
+    else:
+        assert sh.contains_seqs_dev(qd.data_ptr(), np.array([0], dtype=np.uint64)).numel() == 0
     sh.close()
     dist.destroy_process_group()
     print("rank", rank, "ok")
