@@ -84,6 +84,7 @@ SIGNATURES = {
     "cbl_launch_count": (C.c_uint64, []),
     "cbl_sort_fallback_count": (C.c_uint64, []),
     "cbl_build_info": (C.c_char_p, []),
+    "cbl_set_sort_concentration": (C.c_int32, [vp, C.c_double]),
     "cbl_mem_trim": (C.c_int32, [C.c_int32]),
     "cbl_mem_cached_bytes": (C.c_uint64, []),
     "cbl_profile_enable": (None, [C.c_int32]),

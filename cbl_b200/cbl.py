@@ -529,6 +529,10 @@ class CBL:
     def sync(self) -> None:
         self._chk(self._L.cbl_sync(self._h))
 
+    def set_sort_concentration(self, factor: float) -> None:
+        """Planning hint of the batch sort: this handle's words cover ~1 / factor of the prefix mass (a shard of a sharded set)."""
+        self._chk(self._L.cbl_set_sort_concentration(self._h, float(factor)))
+
     def stream_ptr(self) -> int:
         """The cudaStream_t every kernel of this handle is launched on (for CUDA-event timing)."""
         return int(self._L.cbl_stream(self._h) or 0)

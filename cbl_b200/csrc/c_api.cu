@@ -594,6 +594,12 @@ int32_t cbl_profile_report(char* out, size_t cap) {
         memcpy(out, r.c_str(), r.size() + 1);
     });
 }
+int32_t cbl_set_sort_concentration(cbl_t* h, double factor) {
+    return guard(h, [&] {
+        need(h, "handle");
+        h->ix->set_sort_concentration(factor);
+    });
+}
 int32_t cbl_mem_trim(int32_t device) {
     return guard(nullptr, [&] { CUDA_CHECK(cudaSetDevice(device)); arena::trim(); });
 }

@@ -87,6 +87,9 @@ public:
     virtual void bucket_sizes(uint32_t* prefixes, uint32_t* sizes, uint64_t cap, uint64_t* n_out) = 0;
     virtual void load_sorted_words(const uint64_t* lo, const uint64_t* hi, uint64_t n) = 0;
     virtual void sync() = 0;
+    // the batches this handle sorts cover about 1 / factor of the prefix mass (a shard of a prefix-sharded set: factor = number of
+    // shards): the hybrid sort then plans its LSD passes for groups that much denser (plan_sort)
+    virtual void set_sort_concentration(double factor) = 0;
     std::string last_error;
     // words / answers produced by the last sequence call: sum of (len - K + 1) over the records, or fewer when the
     // reads held non-ACGT bytes and the reference's dropping behaviour was reproduced

@@ -79,6 +79,7 @@ class Index final : public IIndex {
     uint32_t last_prefix_ = 0;  // prefix of the last bucket (for the reference's is_empty quirk)
     uint64_t n_dir_ = 0;  // directory words: 32 prefixes each
     uint64_t batch_kmers_;
+    double sort_conc_ = 1.0;    // the batches cover ~1 / sort_conc_ of the prefix mass (set_sort_concentration; grows after a fallback)
     bool sort_hybrid_ = true;   // CBL_SORT=lsd (read once, here): plain LSD passes instead of top passes + segment sort
     static constexpr uint64_t SUF_PAD = 16;  // suffix arrays are over-allocated: probe windows are 32-byte aligned loads
     // pinned host staging of this handle: piece tables on their way in, status words on their way out.  A mutation
@@ -197,6 +198,7 @@ public:
         return nb_ == 1 && last_prefix_ == (uint32_t)((1ull << cfg_.prefix_bits) - 1);
     }
     void sync() override { CUDA_CHECK(cudaSetDevice(cfg_.device)); CUDA_CHECK(cudaStreamSynchronize(st_)); }
+    void set_sort_concentration(double factor) override { sort_conc_ = factor >= 1.0 ? factor : 1.0; }
 
     IndexView<Suf> view() const {
         IndexView<Suf> v;
@@ -216,6 +218,7 @@ public:
     IIndex* clone() override {
         CUDA_CHECK(cudaSetDevice(cfg_.device));
         std::unique_ptr<Index> c(new Index(cfg_));
+        c->sort_conc_ = sort_conc_;
         sync();
         c->copy_state_from(*this);
         c->sync();
@@ -224,7 +227,9 @@ public:
     IIndex* new_empty(int canonical = -1) override {
         Config c = cfg_;
         if (canonical >= 0) c.canonical = canonical;
-        return new Index(c);
+        Index* e = new Index(c);
+        e->sort_conc_ = sort_conc_;
+        return e;
     }
     void copy_state_from(const Index& o) {
         nb_ = o.nb_; n_ = o.n_; last_prefix_ = o.last_prefix_;
@@ -320,11 +325,12 @@ public:
         // The number of passes is chosen so that the largest group of words sharing their sorted top bits fits a segment
         // tile: for k-mer data the most frequent b-bit head of a necklace word has mass ~ 2K / 2^b.  Any other
         // distribution is still sorted exactly: a segment that does not fit raises the fail flag and the batch is
-        // re-sorted by the plain LSD passes.
+        // re-sorted by the plain LSD passes.  A shard of a prefix-sharded set sees only 1 / g of the prefix mass, i.e. heads g
+        // times as frequent: sort_conc_ = g (set by the sharded hosts; it also grows by itself after a fallback).
         if (sort_hybrid_) {
             for (int c = 1; c < sp.n_digits - 1; c++) {   // c LSD passes leave 8 * (n_digits - c) low bits to the segment sort
                 const int b = key_bits - 8 * (sp.n_digits - c);
-                const double est = (double)n * (double)P_.bits / std::ldexp(1.0, b);
+                const double est = (double)n * sort_conc_ * (double)P_.bits / std::ldexp(1.0, b);
                 if (est * 1.5 <= (double)SsTile<W>::T) { sp.n_pass = c; break; }
             }
         }
@@ -647,6 +653,7 @@ public:
         if (h_status_[ST_BAD_BYTE] != ULLONG_MAX) return false;
         if (h_status_[ST_SORT_FAIL]) {   // a group of equal top digits did not fit a segment tile: plain LSD passes (exact for any input)
             g_sort_fallbacks.fetch_add(1, std::memory_order_relaxed);
+            sort_conc_ = std::max(sort_conc_, 1.0) * 256.0;   // the words of this handle are denser than planned: one more LSD pass from now on
             W* other = so.grouped == a ? b : a;
             W* sorted = lsd_passes(so.grouped, other, n, 0, sp.n_digits);
             init_status(stat);

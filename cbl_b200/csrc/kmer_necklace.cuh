@@ -130,14 +130,53 @@ template <class W> CBL_HD void necklace_elim(W w, int bits, W& neck, int& pos) {
     pos = p;
 }
 
+// The same elimination for 64-bit words of 33..63 bits with a cheaper step (the integer ALU pipe is what bounds the
+// kernels; measured per step 15.5 -> 12.5 instructions).  wk holds a 64-bit window of the PERIODIC extension of the ring
+// (bit j = ring bit j mod bits): rotating the ring by one is then  (wk << 1) | (wk >> (bits - 1))  with no masking — the
+// bits shifted in at the bottom are the periodic continuation, and for bits >= 33 they fit the low 32-bit half, so the
+// high half is a plain shift.  cand only ever holds bits below `bits`, so the extension above never shows in cand & ~wk.
+// "More than one candidate left" is tested with population counts (their pipe is idle) instead of cand & (cand - 1).
+#ifndef CBL_NECKLACE_PERIODIC
+#define CBL_NECKLACE_PERIODIC 1
+#endif
+CBL_HD void necklace_elim_periodic(uint64_t w, int bits, uint64_t& neck, int& pos) {
+    const uint64_t mask = low_mask<uint64_t>(bits);
+    uint64_t cand = ~w & mask;
+    if (cand == 0 || w == 0) { neck = w; pos = 0; return; }
+    uint64_t wk = w | (w << bits);   // bits >= 33: two copies cover the 64-bit window
+    const int sh = bits - 1;
+    for (int k = 1; k < bits && popc64(cand) > 1; k += 2) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < 2; u++) {
+            wk = (wk << 1) | (uint64_t)(uint32_t)(wk >> sh);   // 64 - sh <= 32 significant bits come down
+            const uint64_t n = cand & ~wk;
+            if (n != 0) cand = n;
+        }
+    }
+    const int p = bits - 1 - top_bit(cand);
+    neck = rotl_ring<uint64_t>(w, p, bits, mask);
+    pos = p;
+}
+
 template <class W> CBL_HD void necklace_runs(W w, int bits, W& neck, int& pos);
 // 64-bit words take the elimination loop; 128-bit words keep variant 0: the elimination loop compiled for u128 gives
 // wrong words on sm_100a with nvcc 12.9 (GPU parity tests, 2K = 118) although the same source is right on the host —
 // the same class of miscompile as the incremental rotation noted at necklace_brute.
 template <class W> CBL_HD void necklace_fast(W w, int bits, W& neck, int& pos) {
 #if CBL_NECKLACE_ALGO == 1
-    if (sizeof(W) == 8) necklace_elim<W>(w, bits, neck, pos);
-    else necklace_runs<W>(w, bits, neck, pos);
+    if (sizeof(W) == 8) {
+#if CBL_NECKLACE_PERIODIC
+        if (bits >= 33) {
+            uint64_t n64;
+            necklace_elim_periodic((uint64_t)w, bits, n64, pos);
+            neck = (W)n64;
+            return;
+        }
+#endif
+        necklace_elim<W>(w, bits, neck, pos);
+    } else necklace_runs<W>(w, bits, neck, pos);
 #else
     necklace_runs<W>(w, bits, neck, pos);
 #endif

@@ -306,6 +306,7 @@ public:
             Config c = cfg;
             c.device = dev_[d];
             sh_.emplace_back(make_index(c));
+            sh_.back()->set_sort_concentration((double)g_);   // a shard's words cover 1 / g of the prefix mass
         }
         P_ = sh_[0]->params();
         wb_ = (P_.bits + P_.pos_bits) <= 64 ? 8 : 16;
@@ -370,6 +371,7 @@ public:
         return sh_[g_ - 1]->is_empty_reference_semantics();
     }
     void sync() override { for (auto& s : sh_) s->sync(); }
+    void set_sort_concentration(double factor) override { for (auto& s : sh_) s->set_sort_concentration(factor * g_); }
     IIndex* new_empty(int canonical = -1) override {
         Config c = cfg_;
         if (canonical >= 0) c.canonical = canonical;

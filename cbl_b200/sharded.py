@@ -334,6 +334,10 @@ class ShardedCBL:
         self.suffix_bits = 2 * k + pos_bits(k) - prefix_bits
         self.engine = engine if engine is not None else GpuEngine(k, t_bits, prefix_bits, canonical, device)
         self.device = self.engine.device
+        if self.world > 1 and isinstance(self.engine, GpuEngine):
+            # a shard's batches cover 1 / world of the prefix mass: the hybrid batch sort plans for heads that much more frequent
+            # (without the hint the first batch of an 8-GPU shard overflows the segment tiles and is re-sorted by plain LSD passes)
+            self.engine.cbl.set_sort_concentration(self.world)
         if splitters is not None:
             sp = torch.tensor(list(splitters), dtype=torch.int64, device=self.device)
         else:

@@ -207,6 +207,12 @@ uint64_t cbl_launch_count(void);              /* kernels launched by this librar
  * LSD passes: 0 for k-mer data, > 0 only for heavily repeated words (results are identical either way) */
 uint64_t cbl_sort_fallback_count(void);
 const char* cbl_build_info(void);
+/* Planning hint for the batch sort: the words this handle will be given cover about 1 / factor of the prefix mass (a shard of a
+ * set sharded over `factor` GPUs by prefix range: every head of a necklace word is `factor` times as frequent as in a whole set,
+ * so the hybrid sort needs an extra LSD pass before its segment sort).  Results never depend on it: a wrong plan costs one
+ * re-sort by plain LSD passes (cbl_sort_fallback_count), after which the handle corrects the factor itself.  cbl_create_sharded
+ * sets it on its shards; a host that shards across processes (cbl_b200/sharded.py) calls it on every shard handle. */
+int32_t cbl_set_sort_concentration(cbl_t* h, double factor);
 /* device memory: the library keeps the blocks it frees in a per-stream arena (no driver allocation in the steady
  * state; the reference relies on the Rust global allocator the same way).  cbl_mem_trim returns every cached block
  * of `device` to the driver (synchronises the device); cbl_mem_cached_bytes = bytes currently cached. */

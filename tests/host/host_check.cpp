@@ -53,7 +53,7 @@ int main(int argc, char** argv) {
     long n = argc > 1 ? atol(argv[1]) : 200000;
     std::mt19937_64 g(2024);
     long bad = 0;
-    for (int bits : {2, 6, 14, 30, 50, 58}) bad += check_bits<uint64_t>(bits, n, g);
+    for (int bits : {2, 6, 14, 30, 34, 42, 50, 58}) bad += check_bits<uint64_t>(bits, n, g);   // >= 33: the periodic-window step
     for (int bits : {14, 50, 62, 64, 66, 100, 118}) bad += check_bits<u128>(bits, n, g);
     // revcomp + canonical word vs oracle KmerOps (x86 byte-swap formulation, src/kmer.rs:327-348)
     for (int k : {1, 3, 7, 11, 15, 25, 29}) {
