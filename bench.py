@@ -218,6 +218,89 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
+
+_POLL_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+u, idx, period = sys.argv[1], int(sys.argv[2]), float(sys.argv[3])
+try:
+    h = nv.nvmlDeviceGetHandleByUUID(u if u.startswith("GPU-") else "GPU-" + u)
+except Exception:
+    h = nv.nvmlDeviceGetHandleByIndex(idx)
+print("max", float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)), flush=True)
+while True:
+    try:
+        pw = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+    except Exception:
+        pw = -1.0
+    print(time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)), pw, flush=True)
+    time.sleep(period)
+"""
+
+
+def sampler_at(step_i: int, first_timed: int, sampler, world: int, local: int, uuid: str):
+    """Clock sampler of a timed loop, called by rank 0 at the top of every iteration: N = 1 -> the in-process NVML thread,
+    started with the first timed step; N > 1 -> the child-process sampler, started with the first iteration (it needs a moment
+    to come up) and armed with the first timed step."""
+    if world > 1:
+        if step_i == 0 and sampler is None:
+            sampler = ExternalClockSampler(local, uuid)
+        if step_i == first_timed and sampler is not None:
+            sampler.begin()
+    elif step_i == first_timed:
+        sampler = ClockSampler(local, uuid)
+    return sampler
+
+
+class ExternalClockSampler:
+    """The same samples taken by a CHILD process (NVML, 5 ms period), used when N > 1: in the sharded step every phase is
+    host-synchronous, and an in-process NVML thread (driver locks, GIL hand-overs) was seen to hold rank 0 back by tens of
+    milliseconds in some steps, which every other rank then waits for.  Start it early (the child needs a moment to come
+    up), call begin() right before the timed region; stop() keeps the samples taken between begin() and stop()."""
+
+    def __init__(self, gpu_index: int, uuid: str | None = None):
+        self.rows, self.t0 = [], None
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _POLL_SRC, uuid or "", str(gpu_index), "0.005"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.split())
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def stop(self):
+        t1 = time.time()
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml child unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mx = next((float(r[1]) for r in self.rows if r and r[0] == "max"), None)
+        rows = [r for r in self.rows if len(r) == 4 and r[0] != "max" and (self.t0 or 0) <= float(r[0]) <= t1]
+        try:
+            import pynvml as nv
+
+            flags = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+                     "hw_power_brake_slowdown": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+        except Exception:
+            flags = {}
+        reasons = sorted(k for k, f in flags.items() if any(int(r[2]) & f for r in rows))
+        sm = [float(r[1]) for r in rows]
+        pw = [float(r[3]) for r in rows if float(r[3]) >= 0]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm),
+                "power_w_max": max(pw) if pw else None, "source": "nvml in a child process, 5 ms period, timed region only"}
+
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the oracle is the checker / baseline, never the product)
 # ------------------------------------------------------------------------------------------------
@@ -618,8 +701,8 @@ def run_config2(args):
     for s in range(n_ins_warm + n_ins_steps):
         scratch = new_index()
         barrier()
-        if s == n_ins_warm and insert_headline and rank == 0:
-            sampler = ClockSampler(local, str(torch.cuda.get_device_properties(local).uuid))
+        if insert_headline and rank == 0:
+            sampler = sampler_at(s, n_ins_warm, sampler, world, local, str(torch.cuda.get_device_properties(local).uuid))
         st = lib_stream(scratch)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = cbl_b200.launch_count()
@@ -691,10 +774,16 @@ def run_config2(args):
         else:
             cbl.contains_seqs_dev(query.data_ptr(), q_off, answers.data_ptr())
 
+    sampler = None
+    if rank == 0 and not insert_headline and world > 1:
+        sampler = ExternalClockSampler(local, str(torch.cuda.get_device_properties(local).uuid))   # comes up during the warm-up
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local, str(torch.cuda.get_device_properties(local).uuid)) if (rank == 0 and not insert_headline) else None
+    if rank == 0 and not insert_headline and world == 1:
+        sampler = ClockSampler(local, str(torch.cuda.get_device_properties(local).uuid))
+    if isinstance(sampler, ExternalClockSampler):
+        sampler.begin()
     launches0 = cbl_b200.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # the stream the library launches on (sharded: every library call in the step is host-synchronous, so two events on

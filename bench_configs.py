@@ -142,8 +142,8 @@ def _build_steps(cx: Ctx, args, reads, off, n_kmers_total, host_e2e=True):
     keep = None
     for s in range(args.warmup + args.steps):
         c = cx.new_index()
-        if s == args.warmup and cx.rank == 0:
-            sampler = B.ClockSampler(cx.local, str(torch.cuda.get_device_properties(cx.local).uuid))
+        if cx.rank == 0:
+            sampler = B.sampler_at(s, args.warmup, sampler, cx.world, cx.local, str(torch.cuda.get_device_properties(cx.local).uuid))
         l0 = cx.lib.launch_count()
         t = cx.timed(c, lambda: c.insert_seqs_dev(reads.data_ptr(), off))
         if s >= args.warmup:
@@ -286,8 +286,8 @@ def run_setops(args):
     outs = {}
     launches, sampler = 0, None
     for s in range(args.warmup + args.steps):
-        if s == args.warmup and cx.rank == 0:
-            sampler = B.ClockSampler(cx.local, str(torch.cuda.get_device_properties(cx.local).uuid))
+        if cx.rank == 0:
+            sampler = B.sampler_at(s, args.warmup, sampler, cx.world, cx.local, str(torch.cuda.get_device_properties(cx.local).uuid))
         for op, name in enumerate(names):
             c = a.clone()
             l0 = cx.lib.launch_count()
@@ -415,8 +415,8 @@ def run_stream(args):
 
     ms, launches, sampler, hits = [], 0, None, 0
     for s in range(min(args.warmup, 1) + args.steps):
-        if s == min(args.warmup, 1) and cx.rank == 0:
-            sampler = B.ClockSampler(cx.local, str(torch.cuda.get_device_properties(cx.local).uuid))
+        if cx.rank == 0:
+            sampler = B.sampler_at(s, min(args.warmup, 1), sampler, cx.world, cx.local, str(torch.cuda.get_device_properties(cx.local).uuid))
         l0 = cx.lib.launch_count()
         box = {}
         t = cx.timed(c, lambda: box.update(h=stream_once()))
