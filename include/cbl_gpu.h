@@ -22,7 +22,8 @@
  *   - sequences are raw nucleotide bytes (what needletail hands to the reference), batches are a
  *     concatenation + n_seqs+1 byte offsets.  A record shorter than K => CBL_EINVAL (the reference
  *     panics).  Non-ACGT bytes are dropped chunk by chunk exactly like the reference does (see the note at
- *     cbl_last_kmer_count); only the fused multi-GPU route cbl_seq_route_dev rejects them with CBL_EINVAL.
+ *     cbl_last_kmer_count); only the fused multi-GPU kernels (cbl_seq_route_dev, cbl_seq_contains_fused_dev) reject them with
+ *     CBL_EINVAL, and the sharded handle (cbl_create_sharded) then takes its exact slow path through the host.
  */
 #ifndef CBL_GPU_H
 #define CBL_GPU_H
