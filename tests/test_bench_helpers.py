@@ -22,3 +22,18 @@ def test_build_phase_roofline_uses_survey_bytes():
     assert r["merge_apply_kernel"]["algorithmic_bytes_per_launch"] == n * 8 + stored * 4 + 3 * (1 << 24) * 4
     assert 0 < r["seg_sort_kernel"]["frac_of_hbm_peak"] < 1
     assert bench.build_phase_roofline(None, n, stored, peak) is None
+
+
+def test_external_clock_sampler_without_a_gpu():
+    """The child-process sampler of N > 1 runs (bench.ExternalClockSampler) must not take the bench down when NVML is
+    unusable (no driver here): it reports no samples instead."""
+    import time
+
+    import bench
+
+    smp = bench.sampler_at(0, 1, None, 2, 0, "")
+    assert isinstance(smp, bench.ExternalClockSampler)
+    smp = bench.sampler_at(1, 1, smp, 2, 0, "")
+    time.sleep(0.2)
+    out = smp.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"} and not out.get("samples")
