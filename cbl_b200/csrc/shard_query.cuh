@@ -6,7 +6,7 @@
 // (src/wordset/mod.rs:160-185) on the owner.
 //
 // Why one kernel.  On one GPU the integer-bound necklace hides under the memory stalls of the probe because every warp
-// does both (seq_words_kernel MODE 1: 10.2 + 18.3 -> 20.4 ms per 1 G k-mers).  Sharded, a word is made on one GPU and
+// does both (seq_words_kernel MODE 1: 10.2 + 18.3 -> 20.1 ms per 1 G k-mers).  Sharded, a word is made on one GPU and
 // probed on another, and with two kernels (route, then probe; or producer and consumer co-resident with capped grids)
 // the two halves add up: the probe needs ~48 warps per SM to cover its latency, the producer needs the same issue
 // slots, and the register file cannot hold both populations.  Here every resident warp is both: it takes a produce
@@ -21,9 +21,10 @@
 //   straight to the owner.  When all words of s are reserved, s publishes final(s -> d) = epoch << 48 | (words sent + 1)
 //   (low bits all ones if the region ran out of capacity: nothing of the overflow was written); the epoch tag tells the
 //   owner that the value belongs to this call, so the slots need no zeroing (and no barrier) between calls.
-//   owner d: tickets t -> (block t / g of source t % g); a block is complete when all of its SQ_BLOCK words (or, once
-//   final is known, what is left of the region) differ from the sentinel.  The consumer puts the sentinel back as it
-//   reads, so the buffer is clean for the next call.  A warp never waits for a block while produce tasks remain, and
+//   owner d: tickets t -> (block t / g of source t % g); a block is taken up when its LAST word (of SQ_BLOCK or, once
+//   final is known, of what is left of the region) differs from the sentinel: runs are reserved and stored in order, so
+//   the rest has landed or is in flight, and the consumer waits for the odd straggler as it goes through the block.  It
+//   puts the sentinel back as it reads, so the buffer is clean for the next call.  A warp never waits for a block while produce tasks remain, and
 //   producers never wait for consumers, so the kernels of the g ranks cannot deadlock; only after a rank's own
 //   production is finished do its warps spin (with a time-out that raises an error flag) on blocks that other ranks
 //   are still filling.
@@ -34,7 +35,7 @@ namespace cbl {
 
 constexpr int SQ_THREADS = 64;   // two independent warps per CTA (no block-level barrier after the prologue)
 constexpr int SQ_UNIT = 256;     // words staged per flush (8 rounds of 32 k-mers)
-constexpr int SQ_BLOCK = 1024;   // words per consumer block = granularity of the ready counters
+constexpr int SQ_BLOCK = 1024;   // words per consumer block (one ticket)
 constexpr int SQ_HALF = 1024;    // k-mers per produce task: half a reference chunk, lane l packs bases [32 l, 32 l + 32)
 constexpr int SQ_MAX_RANKS = ROUTE_MAX_SPLIT + 1;
 #ifndef CBL_SQ_OPAQUE_IDS
