@@ -500,16 +500,29 @@ class ShardedCBL:
             px.clean_recv()
             epoch = px.next_epoch()
             px.recv_dirty = True           # until the call has come back clean
-            counts = cbl.seq_contains_fused_dev(
-                d_buf, offsets, self.splitters_u32,
-                peer_region=px.my_regions(),
-                peer_final=[px.final_slot(px.peer_ctrl[d], self.rank) for d in range(g)],
-                cap=px.cap, d_pos=pos.data_ptr(),
-                recv_region=[px.recv_region(s_) for s_ in range(g)],
-                answer_region=[px.answer_region(s_) for s_ in range(g)],
-                final_counts=[px.final_slot(px.own_ctrl, s_) for s_ in range(g)],
-                epoch=epoch)
-            C = px.all_counts(counts)                                # barrier: every consumer is done => my answers have landed
+            # a rank whose kernel reports an error (reads with non-ACGT bytes: the fused kernel rejects them) has still run its
+            # share of the protocol to the end; it tells the others through the count exchange, so that every rank raises
+            # instead of the others waiting in a collective for ever
+            failure = None
+            try:
+                counts = cbl.seq_contains_fused_dev(
+                    d_buf, offsets, self.splitters_u32,
+                    peer_region=px.my_regions(),
+                    peer_final=[px.final_slot(px.peer_ctrl[d], self.rank) for d in range(g)],
+                    cap=px.cap, d_pos=pos.data_ptr(),
+                    recv_region=[px.recv_region(s_) for s_ in range(g)],
+                    answer_region=[px.answer_region(s_) for s_ in range(g)],
+                    final_counts=[px.final_slot(px.own_ctrl, s_) for s_ in range(g)],
+                    epoch=epoch)
+            except Exception as e:   # noqa: BLE001 (re-raised below, on every rank)
+                failure, counts = e, np.zeros(g, dtype=np.uint64)
+            full = px.all_counts(np.append(counts, np.uint64(1 if failure is not None else 0)))   # barrier: every consumer is done => my answers have landed
+            C = full[:, :g]
+            if full[:, g].any():
+                if failure is not None:
+                    raise failure
+                bad = [int(r) for r in np.nonzero(full[:, g])[0]]
+                raise RuntimeError(f"sharded contains_seq failed on rank(s) {bad} (see their error); nothing was answered")
             if os.environ.get("CBL_SHARD_TRACE"):
                 print(f"[shard trace] rank {self.rank}: sent {int(C[self.rank].sum())} words, received {int(C[:, self.rank].sum())}", flush=True)
             if int(C.max()) <= px.cap:

@@ -103,6 +103,22 @@ WORKER = textwrap.dedent(
         assert np.array_equal(got, exp) and 0 < got.sum() < len(got)
     else:
         assert sh.contains_seqs_dev(qd.data_ptr(), np.array([0], dtype=np.uint64)).numel() == 0
+    if "fused" in MODE:
+        # reads with a non-nucleotide byte on ONE rank: the fused kernel rejects them, and every rank must see the call fail
+        # (nobody is left waiting in a collective); the set keeps working afterwards
+        q2 = np.concatenate([reads[1][150000:200000], util.random_dna(30000, seed=78)])
+        bad = q2.copy()
+        bad[12345] = ord("N")
+        t_bad = torch.from_numpy(bad if rank == world - 1 else q2).to(dev)
+        try:
+            sh.contains_seqs_dev(t_bad.data_ptr(), np.array([0, len(q2)], dtype=np.uint64))
+            raised = False
+        except Exception:
+            raised = True
+        assert raised, "a rank with non-ACGT reads must fail the call on every rank"
+        t_ok = torch.from_numpy(q2).to(dev)
+        got = sh.contains_seqs_dev(t_ok.data_ptr(), np.array([0, len(q2)], dtype=np.uint64)).cpu().numpy()
+        assert np.array_equal(got, ref.contains_seq(q2))
     sh.close()
     dist.destroy_process_group()
     print("rank", rank, "ok")
