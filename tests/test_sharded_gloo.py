@@ -61,6 +61,30 @@ def test_word_prefixes_and_route():
     assert max(cost) - min(cost) <= 3.0 and edges[1] > 1150 and edges[-1] - edges[-2] < 900
 
 
+def test_cpp_splitters_match_python(tmp_path):
+    """cbl_create_sharded (one process, C++: csrc/splitters.hpp) and ShardedCBL (one process per GPU, Python) must cut the same
+    sample the same way: a set built by one host is then sharded like a set built by the other."""
+    from cbl_b200.sharded import equal_mass_splitters
+
+    exe = str(tmp_path / "splitters_check")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "host", "splitters_check.cpp")], check=True)
+    rng = np.random.default_rng(11)
+    # skewed like necklace prefixes: most of the mass at small values, a long sparse tail
+    sample = np.minimum((rng.exponential(60000.0, size=200_000)).astype(np.uint32) + rng.integers(0, 50, 200_000).astype(np.uint32), (1 << 24) - 1).astype(np.uint32)
+    path = tmp_path / "sample.bin"
+    sample.tofile(path)
+    srt = np.sort(sample)
+    for world in (2, 3, 4, 8, 16):
+        out = subprocess.run([exe, str(path), str(world)], capture_output=True, text=True, check=True).stdout.split()
+        cpp = np.array([int(x) for x in out], dtype=np.int64)
+        py = equal_mass_splitters(torch.from_numpy(sample.astype(np.int64)), world).numpy()
+        assert len(cpp) == world - 1 == len(py)
+        # same cut up to one position of the sorted sample (the two hosts invert the same cost curve in floating point)
+        for a, b in zip(cpp, py):
+            ia, ib = np.searchsorted(srt, a, side="left"), np.searchsorted(srt, b, side="left")
+            assert abs(int(ia) - int(ib)) <= 2, (world, cpp.tolist(), py.tolist())
+
+
 WORKER = textwrap.dedent(
     """
     import os, sys
